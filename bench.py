@@ -1,0 +1,330 @@
+#!/usr/bin/env python
+"""bench.py - ICP iterations/s (whole-job) and Mpoints/s of the J^T J / J^T r reduction on B200.
+
+Contract (see the task statement): `python bench.py --gpus N --steps K --warmup W [--impl reference]`
+prints ONE JSON line on rank 0.  A "step" is one full registration of the C2 workload (synthetic
+100k-point cylinder pair, 50 fixed ICP iterations: correspondences + K1 + K2 every iteration).
+
+  value      ICP iterations/s, source + target resident in HBM when the timed region starts
+  e2e        same metric through the public C-ABI call with HOST buffers: every step uploads the
+             scan from pinned host memory and reads back pose + per-iteration log
+  roofline   K1 (fused residual/weight/Jacobian/27-sum reduction) at C4 size (10M slots, frozen
+             float4 planes, 32 B/slot), CUDA-event timed on the launching stream, vs MEASURED_PEAKS
+  cpu_baseline  the CPU oracle (port of the reference loop) timed on this box's host cores on a
+             bounded sample of the same workload
+N > 1: replicas (one independent scan pair per GPU, no data-path collective, "weak"); the sharded
+10M-slot reduction with its 32-double ncclAllReduce is reported under "sharded".
+`--impl reference` times the reference's own CPU algorithm (oracle port; the reference binary cannot
+be built here: Eigen/PCL/yaml-cpp absent and its "Ours" stage is a stub) on the same config.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+C2_POINTS = 100_000
+C2_ITERS = 50
+C4_SLOTS = 10_000_000
+C4_RADIUS = 0.05
+ALG_BYTES_PER_SLOT = 32          # float4 point + float4 plane
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.path = tempfile.mktemp(suffix=".csv")
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        try:
+            for ln in open(self.path):
+                f = [x.strip() for x in ln.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1])); mx.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), samples=len(sm))
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+def c2_params(default_params):
+    # the reference's published cylinder setup (results/simulation/table3_fig9_fig10): "Ours" =
+    # [SCHUR_CONDITION_NUMBER, PRECONDITIONED_CG], kappa_th = kappa_tg = 10, weight derivative on;
+    # 50 fixed iterations (BASELINE.json configs[1])
+    return default_params(search_radius=1.0, max_iterations=C2_ITERS, fixed_iterations=1, kappa_target=10.0,
+                          cond_thresh=10.0, use_weight_derivative=1, detection="SCHUR_CONDITION_NUMBER",
+                          handling="PRECONDITIONED_CG")
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port on host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_icp_sample(n_points, iters, seed):
+    """Time `iters` full ICP iterations of the oracle on the C2 scene.  Returns (seconds, cores, kind)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    from dcreg_b200.scenes import make_cylinder, g2_initial_pose
+    pts = make_cylinder(n_points, seed=seed)
+    T0 = g2_initial_pose()
+    try:
+        import dcreg_oracle_c as oc          # C/OpenMP port (oracle/dcreg_oracle.c), all host cores
+        if oc.available():
+            return oc.time_icp(pts, pts, T0, iters) + ("port",)
+    except ImportError:
+        pass
+    import dcreg_oracle as o
+    prm = o.Params(max_iterations=iters, conv_rot=0.0, conv_trans=0.0, kappa_target=10.0, use_weight_derivative=True)
+    tree = o.build_tree(pts)                  # kd-tree build is outside the reference's timed region too
+    t0 = time.perf_counter()
+    o.icp_so3(pts, pts, T0, prm, tree)
+    return time.perf_counter() - t0, 1, "port"
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    sample_iters = 3
+    for _ in range(max(0, min(args.warmup, 1))):
+        cpu_icp_sample(C2_POINTS, 1, 42)
+    times = []
+    cores = 1
+    for _ in range(max(1, args.steps)):
+        sec, cores, kind = cpu_icp_sample(C2_POINTS, sample_iters, 42)
+        times.append(sec)
+    tot = float(np.sum(times))
+    value = sample_iters * len(times) / tot
+    line = {
+        "impl": "reference", "metric": "icp_iterations_per_s", "value": value, "unit": "ICP iterations/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot / len(times),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"C2 synthetic cylinder pair {C2_POINTS} pts, Ours (Schur+PCG), search_radius 1.0",
+                   "sample": f"{sample_iters} ICP iterations per step"},
+        "cpu_baseline": {"value": value, "unit": "ICP iterations/s", "cores": cores, "kind": "port",
+                         "sample": f"{sample_iters} iterations x {len(times)} steps of the C2 workload"},
+        "e2e": {"value": value, "unit": "ICP iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+    from dcreg_b200 import Context, default_params
+    from dcreg_b200.scenes import make_cylinder, make_corridor, g2_initial_pose
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - dcreg_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier(device_ids=[local_rank])
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    ctx = Context(local_rank)
+    stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+
+    # ---------------- C2: full ICP iterations/s (replicas at N > 1) ----------------
+    pts = make_cylinder(C2_POINTS, seed=42 + rank)
+    pinned = torch.from_numpy(pts).pin_memory()
+    pts_pinned = pinned.numpy()
+    T0 = g2_initial_pose()
+    prm = c2_params(default_params)
+    ctx.set_target(pts, 1.0)                 # spatial index build: setup, outside the reference's timed region too
+    ctx.set_source(pts_pinned)
+    for _ in range(max(args.warmup, 3)):
+        res = ctx.icp_run(prm, T0, want_log=False)
+    assert res.iterations == C2_ITERS
+
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    l0 = ctx.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for _ in range(args.steps):
+        res = ctx.icp_run(prm, T0, want_log=False)       # inputs resident in HBM
+    e1.record(stream)
+    e1.synchronize()
+    barrier()
+    dev_ms = max_over_ranks(e0.elapsed_time(e1))
+    launches = ctx.launch_count - l0
+    value = world * args.steps * C2_ITERS / (dev_ms * 1e-3)
+
+    # e2e: host buffers in, pose + log out, every step
+    barrier()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    w0 = time.perf_counter()
+    e2.record(stream)
+    for _ in range(args.steps):
+        ctx.set_source(pts_pinned)                        # H2D of this step's scan (pinned)
+        res = ctx.icp_run(prm, T0, want_log=True)         # D2H of pose + per-iteration records
+    e3.record(stream)
+    e3.synchronize()
+    wall = time.perf_counter() - w0
+    barrier()
+    e2e_ms = max_over_ranks(max(e2.elapsed_time(e3), wall * 1e3))
+    clocks = sampler.stop() if rank == 0 else None
+    e2e_value = world * args.steps * C2_ITERS / (e2e_ms * 1e-3)
+    from dcreg_b200.api import IterLog
+    import ctypes
+    h2d = int(pts.shape[0] * 3 * 4 + 16 * 8)
+    d2h = int(ctypes.sizeof(IterLog) * C2_ITERS + 472)
+
+    # ---------------- C4: K1 reduction roofline (sharded at N > 1) ----------------
+    n_total = C4_SLOTS
+    scene = make_corridor(n_total, seed=44, noise=0.002)
+    lo, hi = rank * n_total // world, (rank + 1) * n_total // world
+    Tc = np.eye(4); Tc[:3, 3] = [0.004, 0.003, -0.002]
+    ctx.set_target(scene, C4_RADIUS)
+    ctx.set_source(scene[lo:hi])
+    ctx.set_global_source_count(n_total)
+    ctx.find_planes(Tc, C4_RADIUS, want_planes=False)     # correspondences once; planes stay on the device
+    ctx.freeze_planes_f32()
+    if world > 1:
+        idt = torch.zeros(128, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            idt = torch.tensor(list(ctx.comm_unique_id()), dtype=torch.uint8, device=dev)
+        dist.broadcast(idt, 0)
+        ctx.comm_init(bytes(idt.cpu().tolist()), rank, world)
+    out27, stats = ctx.reduce_device(False, Tc, True)     # warm-up + sanity
+    for _ in range(3):
+        ctx.time_reduce(False, Tc, True, 2, False)
+    barrier()
+    reps = 20
+    k1_ms = max_over_ranks(ctx.time_reduce(False, Tc, True, reps, False))      # inputs (320 MB) > L2 (126 MB)
+    k1_ms_f64 = max_over_ranks(ctx.time_reduce(True, Tc, True, reps, False))
+    barrier()
+    peak, peak_src = measured_peak_gbs()
+    n_local = hi - lo
+    achieved = ALG_BYTES_PER_SLOT * n_local / (k1_ms * 1e-3) / 1e9             # per GPU
+    mpts = n_total / (k1_ms * 1e-3) / 1e6                                       # whole job
+
+    # ---------------- CPU baseline (rank 0, N = 1 only) ----------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sec, cores, kind = cpu_icp_sample(C2_POINTS, 3, 42)
+        cpu = {"value": 3 / sec, "unit": "ICP iterations/s", "cores": cores, "kind": kind,
+               "sample": "3 ICP iterations of the C2 workload (kd-tree build excluded, as in the reference)"}
+
+    if rank == 0:
+        line = {
+            "metric": "icp_iterations_per_s", "value": value, "unit": "ICP iterations/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"C2 synthetic cylinder pair {C2_POINTS} pts x {C2_ITERS} fixed ICP iterations per step, "
+                                   "method Ours (Schur detection + PCG), device hash-grid correspondences",
+                       "parallelism": "replicas (one scan pair per GPU)" if world > 1 else "1 GPU",
+                       "l2": "K1 roofline inputs 320 MB > 126 MB L2; no flush needed",
+                       "roofline_workload": f"C4 synthetic corridor {C4_SLOTS} slots, frozen float4 planes"},
+            "e2e": {"value": e2e_value, "unit": "ICP iterations/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": int(launches),
+            "roofline": {"kernel": "reduce_kernel<float4> (K1)", "bound": "hbm", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "ms_per_launch": k1_ms, "slots_per_launch": n_local, "bytes_per_slot": ALG_BYTES_PER_SLOT},
+            "reduction": {"mpoints_per_s": mpts, "slots_total": n_total, "ms": k1_ms,
+                          "f64_plane_variant_ms": k1_ms_f64,
+                          "f64_plane_variant_gbs": 48 * n_local / (k1_ms_f64 * 1e-3) / 1e9,
+                          "n_effective": int(stats[1]),
+                          "collective": "ncclAllReduce 32 doubles per launch" if world > 1 else None},
+            "cpu_baseline": cpu,
+            "clocks": clocks,
+        }
+        print(json.dumps(line))
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank, local_rank, world = env_int("RANK", 0), env_int("LOCAL_RANK", 0), env_int("WORLD_SIZE", 1)
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,914 @@
+// dcreg_b200.cu - kernels + C ABI of the B200-native ICP / degeneracy engine (see include/dcreg_b200.h).
+//
+// Data layout in HBM (per context):
+//   src      float4[N]   body-frame source points (x,y,z,-), uploaded once per scan
+//   tgt grid float4[M]   target points grouped by hash-grid cell + keys/start/count tables
+//   planes64 double4[N]  (nx,ny,nz,d) per source slot, only materialised for the seams / host-plane mode
+//   planes32 float4[N]   the 32 B/slot frozen-plane layout of the K1 benchmark
+//   partials double[grid][32], acc double[32], state (pose, flags), log records
+// One ICP iteration = two kernels chained on one stream: the iteration kernel (correspondences +
+// residual + Jacobian + 27-sum reduction; the last block to finish reduces the block partials) and the
+// single-warp K2 step (analysis, solve, pose update, convergence flag), so nothing returns to the host
+// inside the loop.  Sharded over GPUs a 32-double ncclAllReduce sits between the two.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/dcreg_b200.h"
+#include "corr.cuh"
+#include "k1_reduce.cuh"
+#include "k2_solve.cuh"
+
+using k2::IcpState;
+using k2::kAcc;
+
+// ------------------------------------------------------------------------------------------------
+// kernels
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+constexpr int kBlock = 256;
+
+__device__ __forceinline__ k1::Pose load_pose(const IcpState* st) {
+    k1::Pose P;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) P.R[i] = st->R[i];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) P.t[i] = st->t[i];
+    return P;
+}
+
+// Ticket: returns true in every thread of the last block to arrive.
+__device__ __forceinline__ bool last_block_ticket(unsigned int* counter) {
+    __shared__ bool is_last;
+    __threadfence();
+    if (threadIdx.x == 0) {
+        const unsigned int t = atomicAdd(counter, 1u);
+        is_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (is_last) __threadfence();
+    return is_last;
+}
+
+struct IterArgs {
+    const float4* src;
+    long long n;
+    corr::Grid grid;
+    IcpState* state;
+    double* partials;
+    unsigned int* counter;
+    double* acc;
+    double4* planes_out;      // optional: materialise the planes (seam 1 / debugging)
+    dcreg_icp_params prm;
+};
+
+// One ICP iteration: stage S1 (correspondences, plane fit, residual, weight) fused with S4-S5
+// (Jacobian, normal equations) and, on one GPU, S6-S9 (analysis, solve, update, convergence).
+__global__ void __launch_bounds__(kBlock) icp_iteration_kernel(IterArgs a) {
+    __shared__ double smem[(kBlock / 32) * kAcc];
+    if (a.state->done) return;
+    const k1::Pose P = load_pose(a.state);
+    k1::Acc acc;
+    k1::acc_zero(acc);
+    const double r2max = a.prm.search_radius * a.prm.search_radius;
+    const bool use_wd = a.prm.use_weight_derivative != 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n;
+         i += (long long)gridDim.x * blockDim.x) {
+        const float4 p4 = __ldg(&a.src[i]);
+        const double px = (double)p4.x, py = (double)p4.y, pz = (double)p4.z;
+        const float qx = (float)(P.R[0] * px + P.R[1] * py + P.R[2] * pz + P.t[0]);
+        const float qy = (float)(P.R[3] * px + P.R[4] * py + P.R[5] * pz + P.t[1]);
+        const float qz = (float)(P.R[6] * px + P.R[7] * py + P.R[8] * pz + P.t[2]);
+        corr::Knn5 nn;
+        corr::knn_init(nn);
+        corr::knn_search(a.grid, qx, qy, qz, nn);
+        double nx = 0.0, ny = 0.0, nz = 0.0, d = 0.0;
+        bool ok = false;
+        if (nn.pos[4] >= 0 && (double)nn.d2[4] < r2max) {            // icp_test_runner.cpp:1726
+            acc.npt += 1;                                              // :1731
+            ok = corr::fit_plane(a.grid, nn, a.prm.min_normal_norm, a.prm.plane_thickness, nx, ny, nz, d);
+        }
+        if (a.planes_out) a.planes_out[i] = ok ? make_double4(nx, ny, nz, d) : make_double4(0.0, 0.0, 0.0, 0.0);
+        k1::accumulate_slot(acc, P, px, py, pz, nx, ny, nz, d, use_wd, ok);
+    }
+    k1::block_reduce_store(acc, smem, a.partials + (size_t)blockIdx.x * kAcc);
+    if (last_block_ticket(a.counter)) {
+        __syncthreads();
+        k1::final_reduce(a.partials, gridDim.x, P.R, smem, a.acc);
+        if (threadIdx.x == 0) *a.counter = 0u;
+    }
+}
+
+// K1 standalone: frozen planes (float4 = 32 B/slot, double4 = 48 B/slot).
+template <typename PlaneT>
+struct PlaneLoad;
+template <>
+struct PlaneLoad<float4> {
+    static __device__ __forceinline__ void get(const float4* p, long long i, double& nx, double& ny, double& nz,
+                                               double& d, bool& has) {
+        const float4 v = __ldg(&p[i]);
+        has = (v.x != 0.0f) || (v.y != 0.0f) || (v.z != 0.0f);
+        nx = (double)v.x; ny = (double)v.y; nz = (double)v.z; d = (double)v.w;
+    }
+};
+template <>
+struct PlaneLoad<double4> {
+    static __device__ __forceinline__ void get(const double4* p, long long i, double& nx, double& ny, double& nz,
+                                               double& d, bool& has) {
+        const double2 a = __ldg(reinterpret_cast<const double2*>(p) + 2 * i);
+        const double2 b = __ldg(reinterpret_cast<const double2*>(p) + 2 * i + 1);
+        has = (a.x != 0.0) || (a.y != 0.0) || (b.x != 0.0);
+        nx = a.x; ny = a.y; nz = b.x; d = b.y;
+    }
+};
+
+struct ReduceArgs {
+    const float4* src;
+    const void* plane;
+    long long n;
+    k1::Pose pose;
+    int use_wd;
+    double* partials;
+    unsigned int* counter;
+    double* acc;
+    IcpState* state;          // when non-null: pose is read from state (ICP loop, host-plane mode)
+};
+
+constexpr int kK1Unroll = 4;
+
+template <typename PlaneT>
+__global__ void __launch_bounds__(kBlock) reduce_kernel(ReduceArgs a) {
+    __shared__ double smem[(kBlock / 32) * kAcc];
+    if (a.state && a.state->done) return;
+    const k1::Pose P = a.state ? load_pose(a.state) : a.pose;
+    const PlaneT* plane = reinterpret_cast<const PlaneT*>(a.plane);
+    k1::Acc acc;
+    k1::acc_zero(acc);
+    const bool use_wd = a.use_wd != 0;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    // main loop: kK1Unroll independent slots per thread, all loads issued before the FP64 work
+    for (; i + (kK1Unroll - 1) * stride < a.n; i += kK1Unroll * stride) {
+        float4 p4[kK1Unroll];
+        double nx[kK1Unroll], ny[kK1Unroll], nz[kK1Unroll], d[kK1Unroll];
+        bool has[kK1Unroll];
+#pragma unroll
+        for (int u = 0; u < kK1Unroll; ++u) p4[u] = __ldg(&a.src[i + u * stride]);
+#pragma unroll
+        for (int u = 0; u < kK1Unroll; ++u) PlaneLoad<PlaneT>::get(plane, i + u * stride, nx[u], ny[u], nz[u], d[u], has[u]);
+#pragma unroll
+        for (int u = 0; u < kK1Unroll; ++u) {
+            acc.npt += has[u] ? 1 : 0;
+            k1::accumulate_slot(acc, P, (double)p4[u].x, (double)p4[u].y, (double)p4[u].z, nx[u], ny[u], nz[u],
+                                d[u], use_wd, has[u]);
+        }
+    }
+    for (; i < a.n; i += stride) {
+        const float4 p4 = __ldg(&a.src[i]);
+        double nx, ny, nz, d;
+        bool has;
+        PlaneLoad<PlaneT>::get(plane, i, nx, ny, nz, d, has);
+        acc.npt += has ? 1 : 0;
+        k1::accumulate_slot(acc, P, (double)p4.x, (double)p4.y, (double)p4.z, nx, ny, nz, d, use_wd, has);
+    }
+    k1::block_reduce_store(acc, smem, a.partials + (size_t)blockIdx.x * kAcc);
+    if (last_block_ticket(a.counter)) {
+        __syncthreads();
+        k1::final_reduce(a.partials, gridDim.x, P.R, smem, a.acc);
+        if (threadIdx.x == 0) *a.counter = 0u;
+    }
+}
+
+// K2 as its own kernel (seam 3, and the sharded loop after the all-reduce).
+__global__ void k2_step_kernel(const double* acc, IcpState* st, dcreg_icp_params prm, dcreg_iter_log* log,
+                               int log_cap) {
+    if (threadIdx.x != 0 || st->done) return;
+    k2::icp_step(acc, st, prm, log, log_cap);
+}
+
+__global__ void k2_analyze_kernel(const double* v27, dcreg_icp_params prm, dcreg_analysis* out, double* dx) {
+    if (threadIdx.x != 0) return;
+    k2::analyze_and_solve(v27, prm, out, dx);
+}
+
+__global__ void pcg_kernel(const double* A, const double* b, const double* P, int max_it, double tol, double* x,
+                           int* iters) {
+    if (threadIdx.x != 0) return;
+    double res;
+    *iters = k2::pcg6(A, b, P, max_it, tol, x, &res);
+}
+
+// icp_test_runner.cpp:2014-2037
+__global__ void covariance_kernel(const IcpState* st, double* cov) {
+    if (threadIdx.x != 0) return;
+    bool ok = false;
+    if (st->converged) {
+        double A[36], Inv[36];
+        for (int i = 0; i < 36; ++i) A[i] = st->H_last[i];
+        if (dla::fullpiv_inverse<6>(A, Inv)) {
+            ok = true;
+            double W[36], lam[6], V[36];
+            for (int i = 0; i < 6; ++i)
+                for (int j = 0; j < 6; ++j) W[i * 6 + j] = 0.5 * (Inv[i * 6 + j] + Inv[j * 6 + i]);
+            dla::jacobi_eigh<6>(W, lam, V);
+            if (lam[0] <= 1e-12) {
+                for (int i = 0; i < 6; ++i) lam[i] = fmax(lam[i], 1e-9);
+                for (int i = 0; i < 6; ++i)
+                    for (int j = 0; j < 6; ++j) {
+                        double s = 0.0;
+                        for (int k = 0; k < 6; ++k) s += V[i * 6 + k] * lam[k] * V[j * 6 + k];
+                        cov[i * 6 + j] = s;
+                    }
+            } else {
+                for (int i = 0; i < 36; ++i) cov[i] = Inv[i];
+            }
+        }
+    }
+    if (!ok)
+        for (int i = 0; i < 36; ++i) cov[i] = (i % 7 == 0) ? 1e6 : 0.0;
+}
+
+__global__ void pack_source_kernel(const float* __restrict__ in, long long n, int stride, float4* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    out[i] = make_float4(in[i * stride], in[i * stride + 1], in[i * stride + 2], 0.0f);
+}
+
+__global__ void planes_to_f32_kernel(const double4* __restrict__ in, long long n, float4* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double4 v = in[i];
+    out[i] = make_float4((float)v.x, (float)v.y, (float)v.z, (float)v.w);
+}
+
+__global__ void flush_l2_kernel(float4* buf, long long n, float v) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        buf[i] = make_float4(v, v, v, v);
+}
+
+__global__ void init_state_kernel(IcpState* st, const double* T, long long n_total, unsigned int* counter) {
+    if (threadIdx.x != 0) return;
+    for (int r = 0; r < 3; ++r) {
+        for (int c = 0; c < 3; ++c) st->R[r * 3 + c] = T[r * 4 + c];
+        st->t[r] = T[r * 4 + 3];
+    }
+    st->iter = 0; st->done = 0; st->converged = 0; st->status = DCREG_OK;
+    for (int i = 0; i < 36; ++i) st->H_last[i] = (i % 7 == 0) ? 1.0 : 0.0;
+    st->n_source_total = n_total;
+    *counter = 0u;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// NCCL through dlopen (so the library loads without it; torch's bundled copy is reused when present)
+// ------------------------------------------------------------------------------------------------
+namespace {
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+struct NcclApi {
+    void* lib = nullptr;
+    int (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    int (*CommDestroy)(ncclComm_t) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    bool load(std::string& err) {
+        if (lib) return true;
+        const char* names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char* nm : names) {
+            lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+            if (lib) break;
+        }
+        if (!lib) { err = std::string("dlopen libnccl failed: ") + dlerror(); return false; }
+        GetUniqueId = (int (*)(ncclUniqueId*))dlsym(lib, "ncclGetUniqueId");
+        CommInitRank = (int (*)(ncclComm_t*, int, ncclUniqueId, int))dlsym(lib, "ncclCommInitRank");
+        CommDestroy = (int (*)(ncclComm_t))dlsym(lib, "ncclCommDestroy");
+        AllReduce = (int (*)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t))dlsym(lib, "ncclAllReduce");
+        GetErrorString = (const char* (*)(int))dlsym(lib, "ncclGetErrorString");
+        if (!GetUniqueId || !CommInitRank || !CommDestroy || !AllReduce) { err = "libnccl: missing symbols"; return false; }
+        return true;
+    }
+};
+NcclApi g_nccl;
+constexpr int kNcclFloat64 = 8;   // ncclDouble
+constexpr int kNcclSum = 0;
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------------
+struct dcreg_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    long long launches = 0;
+
+    float4* d_src = nullptr; long long n_src = 0; long long n_src_cap = 0; long long n_src_total = 0;
+    float* d_stage = nullptr; size_t stage_bytes = 0;
+
+    float4* d_tgt = nullptr; long long n_tgt = 0;
+    corr::Grid grid{}; unsigned int grid_capacity = 0; bool has_grid = false;
+    double cell_size = 0.0;
+
+    double4* d_planes64 = nullptr; float4* d_planes32 = nullptr; long long planes_cap = 0;
+
+    double* d_partials = nullptr; int partials_blocks = 0;
+    unsigned int* d_counter = nullptr;
+    double* d_acc = nullptr;
+    IcpState* d_state = nullptr;
+    dcreg_iter_log* d_log = nullptr; int log_cap = 0;
+    double* d_small = nullptr;       // scratch for the seams (>= 512 doubles)
+    dcreg_analysis* d_analysis = nullptr;
+    float4* d_flush = nullptr; long long flush_n = 0;
+
+    void* h_pinned = nullptr; size_t pinned_bytes = 0;
+
+    ncclComm_t comm = nullptr; int rank = 0, nranks = 1;
+};
+
+namespace {
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_);                         \
+            return DCREG_CUDA_ERROR;                                                               \
+        }                                                                                          \
+    } while (0)
+
+int ensure_pinned(dcreg_ctx* ctx, size_t bytes) {
+    if (ctx->pinned_bytes >= bytes) return DCREG_OK;
+    if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+    ctx->h_pinned = nullptr; ctx->pinned_bytes = 0;
+    CK(cudaMallocHost(&ctx->h_pinned, bytes));
+    ctx->pinned_bytes = bytes;
+    return DCREG_OK;
+}
+
+int ensure_partials(dcreg_ctx* ctx, int blocks) {
+    if (ctx->partials_blocks >= blocks) return DCREG_OK;
+    if (ctx->d_partials) cudaFree(ctx->d_partials);
+    ctx->d_partials = nullptr;
+    CK(cudaMalloc(&ctx->d_partials, (size_t)blocks * kAcc * sizeof(double)));
+    ctx->partials_blocks = blocks;
+    return DCREG_OK;
+}
+
+int ensure_planes(dcreg_ctx* ctx, long long n) {
+    if (ctx->planes_cap >= n) return DCREG_OK;
+    if (ctx->d_planes64) cudaFree(ctx->d_planes64);
+    if (ctx->d_planes32) cudaFree(ctx->d_planes32);
+    ctx->d_planes64 = nullptr; ctx->d_planes32 = nullptr; ctx->planes_cap = 0;
+    CK(cudaMalloc(&ctx->d_planes64, (size_t)n * sizeof(double4)));
+    CK(cudaMalloc(&ctx->d_planes32, (size_t)n * sizeof(float4)));
+    ctx->planes_cap = n;
+    return DCREG_OK;
+}
+
+int ensure_log(dcreg_ctx* ctx, int cap) {
+    if (ctx->log_cap >= cap) return DCREG_OK;
+    if (ctx->d_log) cudaFree(ctx->d_log);
+    ctx->d_log = nullptr; ctx->log_cap = 0;
+    CK(cudaMalloc(&ctx->d_log, (size_t)cap * sizeof(dcreg_iter_log)));
+    ctx->log_cap = cap;
+    return DCREG_OK;
+}
+
+// grid size for streaming kernels: a multiple of the SM count
+int stream_grid(const dcreg_ctx* ctx, long long n, int per_sm) {
+    long long need = (n + kBlock - 1) / kBlock;
+    long long cap = (long long)ctx->sm_count * per_sm;
+    if (need < 1) need = 1;
+    return (int)(need < cap ? need : cap);
+}
+
+int upload_points(dcreg_ctx* ctx, const float* xyz, long long n, int stride, float4* d_out) {
+    const size_t bytes = (size_t)n * stride * sizeof(float);
+    if (ctx->stage_bytes < bytes) {
+        if (ctx->d_stage) cudaFree(ctx->d_stage);
+        ctx->d_stage = nullptr; ctx->stage_bytes = 0;
+        CK(cudaMalloc(&ctx->d_stage, bytes));
+        ctx->stage_bytes = bytes;
+    }
+    CK(cudaMemcpyAsync(ctx->d_stage, xyz, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    pack_source_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_stage, n, stride, d_out);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return DCREG_OK;
+}
+
+int launch_reduce(dcreg_ctx* ctx, const float4* d_src, const void* d_plane, bool f64, long long n,
+                  const k1::Pose* pose, int use_wd, IcpState* state) {
+    const int grid = stream_grid(ctx, (n + kK1Unroll - 1) / kK1Unroll, 8);
+    int rc = ensure_partials(ctx, grid);
+    if (rc) return rc;
+    ReduceArgs a{};
+    a.src = d_src; a.plane = d_plane; a.n = n;
+    if (pose) a.pose = *pose;
+    a.use_wd = use_wd; a.partials = ctx->d_partials; a.counter = ctx->d_counter; a.acc = ctx->d_acc;
+    a.state = state;
+    if (f64) reduce_kernel<double4><<<grid, kBlock, 0, ctx->stream>>>(a);
+    else reduce_kernel<float4><<<grid, kBlock, 0, ctx->stream>>>(a);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return DCREG_OK;
+}
+
+int nccl_allreduce_acc(dcreg_ctx* ctx) {
+    if (!ctx->comm) return DCREG_OK;
+    int r = g_nccl.AllReduce(ctx->d_acc, ctx->d_acc, kAcc, kNcclFloat64, kNcclSum, ctx->comm, ctx->stream);
+    if (r != 0) {
+        ctx->err = std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error");
+        return DCREG_NCCL_ERROR;
+    }
+    return DCREG_OK;
+}
+
+int read_results(dcreg_ctx* ctx, double* T_out, dcreg_iter_log* log, int log_cap, int* n_iterations,
+                 int* converged, int* status_out) {
+    int rc = ensure_pinned(ctx, sizeof(IcpState));
+    if (rc) return rc;
+    IcpState* hs = (IcpState*)ctx->h_pinned;
+    CK(cudaMemcpyAsync(hs, ctx->d_state, sizeof(IcpState), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const int iters = hs->iter;
+    if (T_out) {
+        for (int r = 0; r < 3; ++r) {
+            for (int c = 0; c < 3; ++c) T_out[r * 4 + c] = hs->R[r * 3 + c];
+            T_out[r * 4 + 3] = hs->t[r];
+        }
+        T_out[12] = T_out[13] = T_out[14] = 0.0; T_out[15] = 1.0;
+    }
+    if (n_iterations) *n_iterations = iters;
+    if (converged) *converged = hs->converged;
+    *status_out = hs->status;
+    if (log && log_cap > 0) {
+        int nrec = iters < log_cap ? iters : log_cap;
+        // a NOT_ENOUGH_POINTS abort still wrote a record at index iters-1; a NONFINITE abort at index iters
+        if (hs->status == DCREG_NONFINITE_UPDATE && iters < log_cap) nrec = iters + 1;
+        if (nrec > 0) {
+            CK(cudaMemcpyAsync(log, ctx->d_log, (size_t)nrec * sizeof(dcreg_iter_log), cudaMemcpyDeviceToHost,
+                               ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+        }
+    }
+    return DCREG_OK;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+int dcreg_abi_version(void) { return DCREG_ABI_VERSION; }
+
+void dcreg_default_params(dcreg_icp_params* p) {
+    if (!p) return;
+    memset(p, 0, sizeof(*p));
+    p->search_radius = 1.0; p->max_iterations = 30;
+    p->detection = DCREG_DET_SCHUR_CONDITION_NUMBER; p->handling = DCREG_HAND_PRECONDITIONED_CG;
+    p->use_weight_derivative = 0;
+    p->conv_thresh_rot = 1e-5; p->conv_thresh_trans = 1e-3;
+    p->cond_thresh = 10.0; p->eig_thresh = 120.0; p->kappa_target = 1.0;
+    p->pcg_tol = 1e-6; p->pcg_max_iter = 10; p->std_reg_gamma = 0.01;
+    p->plane_thickness = 0.2; p->weight_slope = 0.9; p->weight_gate = 0.1; p->min_normal_norm = 1e-6;
+    p->min_effective_points = 10; p->fixed_iterations = 0;
+}
+
+int dcreg_create(int device_id, dcreg_ctx** out) {
+    if (!out) return DCREG_BAD_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return DCREG_NO_DEVICE;   // no CPU fallback
+    if (device_id < 0 || device_id >= ndev) return DCREG_BAD_ARG;
+    dcreg_ctx* ctx = new dcreg_ctx();
+    ctx->device = device_id;
+    *out = ctx;   // returned even on failure so the caller can read dcreg_last_error
+    CK(cudaSetDevice(device_id));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device_id));
+    ctx->sm_count = prop.multiProcessorCount;
+    CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    CK(cudaMalloc(&ctx->d_counter, sizeof(unsigned int)));
+    CK(cudaMemsetAsync(ctx->d_counter, 0, sizeof(unsigned int), ctx->stream));
+    CK(cudaMalloc(&ctx->d_acc, kAcc * sizeof(double)));
+    CK(cudaMalloc(&ctx->d_state, sizeof(IcpState)));
+    CK(cudaMemsetAsync(ctx->d_state, 0, sizeof(IcpState), ctx->stream));
+    CK(cudaMalloc(&ctx->d_small, 1024 * sizeof(double)));
+    CK(cudaMalloc(&ctx->d_analysis, sizeof(dcreg_analysis)));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return DCREG_OK;
+}
+
+int dcreg_destroy(dcreg_ctx* ctx) {
+    if (!ctx) return DCREG_BAD_ARG;
+    cudaSetDevice(ctx->device);
+    if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    void* ptrs[] = {ctx->d_src, ctx->d_stage, ctx->d_tgt, ctx->grid.keys, ctx->grid.cell_start, ctx->grid.cell_count,
+                    ctx->grid.pts, ctx->d_planes64, ctx->d_planes32, ctx->d_partials, ctx->d_counter, ctx->d_acc,
+                    ctx->d_state, ctx->d_log, ctx->d_small, ctx->d_analysis, ctx->d_flush};
+    for (void* p : ptrs)
+        if (p) cudaFree(p);
+    if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return DCREG_OK;
+}
+
+const char* dcreg_last_error(const dcreg_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+void* dcreg_stream(dcreg_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+int64_t dcreg_launch_count(const dcreg_ctx* ctx) { return ctx ? ctx->launches : 0; }
+void* dcreg_device_source(dcreg_ctx* ctx) { return ctx ? ctx->d_src : nullptr; }
+void* dcreg_device_planes_f64(dcreg_ctx* ctx) { return ctx ? ctx->d_planes64 : nullptr; }
+void* dcreg_device_planes_f32(dcreg_ctx* ctx) { return ctx ? ctx->d_planes32 : nullptr; }
+
+int dcreg_set_source(dcreg_ctx* ctx, const float* xyz, int64_t n, int stride) {
+    if (!ctx) return DCREG_BAD_ARG;
+    if (!xyz || n <= 0 || stride < 3) { ctx->err = "dcreg_set_source: empty cloud or stride < 3"; return DCREG_BAD_ARG; }
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->n_src_cap < n) {
+        if (ctx->d_src) cudaFree(ctx->d_src);
+        ctx->d_src = nullptr; ctx->n_src_cap = 0;
+        CK(cudaMalloc(&ctx->d_src, (size_t)n * sizeof(float4)));
+        ctx->n_src_cap = n;
+    }
+    ctx->n_src = n;
+    if (ctx->nranks == 1) ctx->n_src_total = n;
+    return upload_points(ctx, xyz, n, stride, ctx->d_src);
+}
+
+int dcreg_set_global_source_count(dcreg_ctx* ctx, int64_t n_total) {
+    if (!ctx || n_total <= 0) return DCREG_BAD_ARG;
+    ctx->n_src_total = n_total;
+    return DCREG_OK;
+}
+
+int dcreg_set_target(dcreg_ctx* ctx, const float* xyz, int64_t m, int stride, double cell_size) {
+    if (!ctx) return DCREG_BAD_ARG;
+    if (!xyz || m <= 0 || stride < 3 || !(cell_size > 0.0) || m > 0x7fffffffLL) {
+        ctx->err = "dcreg_set_target: empty cloud, stride < 3, cell_size <= 0 or too many points";
+        return DCREG_BAD_ARG;
+    }
+    CK(cudaSetDevice(ctx->device));
+    void* old[] = {ctx->d_tgt, ctx->grid.keys, ctx->grid.cell_start, ctx->grid.cell_count, ctx->grid.pts};
+    for (void* p : old)
+        if (p) cudaFree(p);
+    ctx->d_tgt = nullptr; ctx->grid = corr::Grid{}; ctx->has_grid = false;
+    CK(cudaMalloc(&ctx->d_tgt, (size_t)m * sizeof(float4)));
+    ctx->n_tgt = m;
+    int rc = upload_points(ctx, xyz, m, stride, ctx->d_tgt);
+    if (rc) return rc;
+    unsigned int cap = 1024;
+    while ((long long)cap < 2 * m) cap <<= 1;
+    ctx->grid_capacity = cap;
+    corr::Grid& g = ctx->grid;
+    g.mask = cap - 1; g.n = (int)m; g.inv_cell = 1.0 / cell_size;
+    ctx->cell_size = cell_size;
+    CK(cudaMalloc(&g.keys, (size_t)cap * sizeof(unsigned long long)));
+    CK(cudaMalloc(&g.cell_start, (size_t)cap * sizeof(int)));
+    CK(cudaMalloc(&g.cell_count, (size_t)cap * sizeof(int)));
+    CK(cudaMalloc(&g.pts, (size_t)m * sizeof(float4)));
+    int *pt_slot = nullptr, *fill = nullptr, *tile_sums = nullptr;
+    const int ntiles = (int)((cap + corr::kScanTile - 1) / corr::kScanTile);
+    CK(cudaMalloc(&pt_slot, (size_t)m * sizeof(int)));
+    CK(cudaMalloc(&fill, (size_t)cap * sizeof(int)));
+    CK(cudaMalloc(&tile_sums, (size_t)ntiles * sizeof(int)));
+    CK(cudaMemsetAsync(g.keys, 0xff, (size_t)cap * sizeof(unsigned long long), ctx->stream));
+    CK(cudaMemsetAsync(g.cell_count, 0, (size_t)cap * sizeof(int), ctx->stream));
+    CK(cudaMemsetAsync(fill, 0, (size_t)cap * sizeof(int), ctx->stream));
+    const unsigned nb = (unsigned)((m + 255) / 256);
+    corr::grid_insert_kernel<<<nb, 256, 0, ctx->stream>>>(ctx->d_tgt, (int)m, g, pt_slot);
+    corr::scan_tile_sums_kernel<<<ntiles, 256, 0, ctx->stream>>>(g.cell_count, (int)cap, tile_sums);
+    corr::scan_tile_offsets_kernel<<<1, 1024, 0, ctx->stream>>>(tile_sums, ntiles);
+    corr::scan_tile_apply_kernel<<<ntiles, 256, 0, ctx->stream>>>(g.cell_count, (int)cap, tile_sums, g.cell_start);
+    corr::grid_scatter_kernel<<<nb, 256, 0, ctx->stream>>>(ctx->d_tgt, (int)m, g, pt_slot, fill);
+    corr::grid_sort_cells_kernel<<<(cap + 255) / 256, 256, 0, ctx->stream>>>(g, cap);
+    ctx->launches += 6;
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(pt_slot); cudaFree(fill); cudaFree(tile_sums);
+    if (e != cudaSuccess) { ctx->err = std::string("grid build: ") + cudaGetErrorString(e); return DCREG_CUDA_ERROR; }
+    CK(cudaGetLastError());
+    ctx->has_grid = true;
+    return DCREG_OK;
+}
+
+static int launch_iteration(dcreg_ctx* ctx, const dcreg_icp_params* prm, double4* planes_out) {
+    const int grid = stream_grid(ctx, ctx->n_src, 16);
+    int rc = ensure_partials(ctx, grid);
+    if (rc) return rc;
+    IterArgs a{};
+    a.src = ctx->d_src; a.n = ctx->n_src; a.grid = ctx->grid; a.state = ctx->d_state;
+    a.partials = ctx->d_partials; a.counter = ctx->d_counter; a.acc = ctx->d_acc;
+    a.planes_out = planes_out; a.prm = *prm;
+    icp_iteration_kernel<<<grid, kBlock, 0, ctx->stream>>>(a);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return DCREG_OK;
+}
+
+static int init_state(dcreg_ctx* ctx, const double T[16]) {
+    CK(cudaMemcpyAsync(ctx->d_small, T, 16 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    init_state_kernel<<<1, 32, 0, ctx->stream>>>(ctx->d_state, ctx->d_small, ctx->n_src_total, ctx->d_counter);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return DCREG_OK;
+}
+
+int dcreg_find_planes(dcreg_ctx* ctx, const double T[16], double search_radius, double* planes_out,
+                      int64_t* n_corr_pt) {
+    if (!ctx || !T) return DCREG_BAD_ARG;
+    if (!ctx->d_src || !ctx->has_grid) { ctx->err = "dcreg_find_planes: set source and target first"; return DCREG_BAD_ARG; }
+    CK(cudaSetDevice(ctx->device));
+    int rc = ensure_planes(ctx, ctx->n_src);
+    if (rc) return rc;
+    dcreg_icp_params prm;
+    dcreg_default_params(&prm);
+    prm.search_radius = search_radius;
+    prm.min_effective_points = 0;
+    if ((rc = init_state(ctx, T))) return rc;
+    if ((rc = launch_iteration(ctx, &prm, ctx->d_planes64))) return rc;
+    double acc[kAcc];
+    CK(cudaMemcpyAsync(acc, ctx->d_acc, sizeof(acc), cudaMemcpyDeviceToHost, ctx->stream));
+    if (planes_out)
+        CK(cudaMemcpyAsync(planes_out, ctx->d_planes64, (size_t)ctx->n_src * sizeof(double4), cudaMemcpyDeviceToHost,
+                           ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (n_corr_pt) *n_corr_pt = (int64_t)(acc[k2::kAccNpt] + 0.5);
+    return DCREG_OK;
+}
+
+static int reduce_common(dcreg_ctx* ctx, const void* d_src, const void* d_plane, bool f64, int64_t n,
+                         const double pose_Rt[12], int use_wd, double out27[27], double stats[3]) {
+    if (!ctx) return DCREG_BAD_ARG;
+    if (!d_src || !d_plane || n <= 0 || !pose_Rt || !out27) { ctx->err = "reduce: null pointer or n <= 0"; return DCREG_BAD_ARG; }
+    CK(cudaSetDevice(ctx->device));
+    k1::Pose P;
+    for (int i = 0; i < 9; ++i) P.R[i] = pose_Rt[i];
+    for (int i = 0; i < 3; ++i) P.t[i] = pose_Rt[9 + i];
+    int rc = launch_reduce(ctx, (const float4*)d_src, d_plane, f64, n, &P, use_wd, nullptr);
+    if (rc) return rc;
+    if ((rc = nccl_allreduce_acc(ctx))) return rc;
+    double acc[kAcc];
+    CK(cudaMemcpyAsync(acc, ctx->d_acc, sizeof(acc), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < 27; ++i) out27[i] = acc[i];
+    if (stats) { stats[0] = acc[k2::kAccSumR2]; stats[1] = acc[k2::kAccNeff]; stats[2] = acc[k2::kAccNpt]; }
+    return DCREG_OK;
+}
+
+int dcreg_reduce_normal_equations(dcreg_ctx* ctx, const void* d_src, const void* d_plane, int64_t n,
+                                  const double pose_Rt[12], int use_weight_derivative, double out27[27],
+                                  double stats[3]) {
+    return reduce_common(ctx, d_src, d_plane, false, n, pose_Rt, use_weight_derivative, out27, stats);
+}
+
+int dcreg_reduce_normal_equations_f64plane(dcreg_ctx* ctx, const void* d_src, const void* d_plane, int64_t n,
+                                           const double pose_Rt[12], int use_weight_derivative, double out27[27],
+                                           double stats[3]) {
+    return reduce_common(ctx, d_src, d_plane, true, n, pose_Rt, use_weight_derivative, out27, stats);
+}
+
+int dcreg_reduce_normal_equations_host(dcreg_ctx* ctx, const float* src4, const void* plane4, int plane_is_f64,
+                                       int64_t n, const double pose_Rt[12], int use_weight_derivative,
+                                       double out27[27], double stats[3]) {
+    if (!ctx) return DCREG_BAD_ARG;
+    if (!src4 || !plane4 || n <= 0) { ctx->err = "reduce_host: null pointer or n <= 0"; return DCREG_BAD_ARG; }
+    CK(cudaSetDevice(ctx->device));
+    int rc = dcreg_set_source(ctx, src4, n, 4);
+    if (rc) return rc;
+    if ((rc = ensure_planes(ctx, n))) return rc;
+    if (plane_is_f64)
+        CK(cudaMemcpyAsync(ctx->d_planes64, plane4, (size_t)n * sizeof(double4), cudaMemcpyHostToDevice, ctx->stream));
+    else
+        CK(cudaMemcpyAsync(ctx->d_planes32, plane4, (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+    return reduce_common(ctx, ctx->d_src, plane_is_f64 ? (const void*)ctx->d_planes64 : (const void*)ctx->d_planes32,
+                         plane_is_f64 != 0, n, pose_Rt, use_weight_derivative, out27, stats);
+}
+
+int dcreg_freeze_planes_f32(dcreg_ctx* ctx) {
+    if (!ctx || !ctx->d_planes64 || ctx->n_src <= 0) return DCREG_BAD_ARG;
+    CK(cudaSetDevice(ctx->device));
+    planes_to_f32_kernel<<<(unsigned)((ctx->n_src + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_planes64, ctx->n_src,
+                                                                                        ctx->d_planes32);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(ctx->stream));
+    return DCREG_OK;
+}
+
+int dcreg_time_reduce(dcreg_ctx* ctx, int plane_is_f64, const double pose_Rt[12], int use_weight_derivative,
+                      int reps, int flush_l2, float* ms_per_launch) {
+    if (!ctx || !pose_Rt || reps <= 0 || !ms_per_launch) return DCREG_BAD_ARG;
+    if (!ctx->d_src || !ctx->d_planes64) { ctx->err = "time_reduce: no source/planes on the context"; return DCREG_BAD_ARG; }
+    CK(cudaSetDevice(ctx->device));
+    k1::Pose P;
+    for (int i = 0; i < 9; ++i) P.R[i] = pose_Rt[i];
+    for (int i = 0; i < 3; ++i) P.t[i] = pose_Rt[9 + i];
+    if (flush_l2 && !ctx->d_flush) {
+        ctx->flush_n = (256ll << 20) / sizeof(float4);   // 256 MiB > 126 MB L2
+        CK(cudaMalloc(&ctx->d_flush, (size_t)ctx->flush_n * sizeof(float4)));
+    }
+    std::vector<cudaEvent_t> e0(reps), e1(reps);
+    for (int i = 0; i < reps; ++i) { CK(cudaEventCreate(&e0[i])); CK(cudaEventCreate(&e1[i])); }
+    const void* plane = plane_is_f64 ? (const void*)ctx->d_planes64 : (const void*)ctx->d_planes32;
+    int rc = DCREG_OK;
+    for (int i = 0; i < reps && rc == DCREG_OK; ++i) {
+        if (flush_l2) {
+            flush_l2_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(ctx->d_flush, ctx->flush_n, (float)i);
+            ctx->launches++;
+        }
+        CK(cudaEventRecord(e0[i], ctx->stream));
+        rc = launch_reduce(ctx, ctx->d_src, plane, plane_is_f64 != 0, ctx->n_src, &P, use_weight_derivative, nullptr);
+        if (rc == DCREG_OK) rc = nccl_allreduce_acc(ctx);      // sharded: the 32-double all-reduce is part of the step
+        CK(cudaEventRecord(e1[i], ctx->stream));
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    double total = 0.0;
+    for (int i = 0; i < reps; ++i) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0[i], e1[i]);
+        total += ms;
+        cudaEventDestroy(e0[i]); cudaEventDestroy(e1[i]);
+    }
+    *ms_per_launch = (float)(total / reps);
+    return rc;
+}
+
+int dcreg_analyze_and_solve(dcreg_ctx* ctx, const double H27[27], const dcreg_icp_params* params,
+                            dcreg_analysis* out, double dx[6]) {
+    if (!ctx) return DCREG_BAD_ARG;
+    if (!H27 || !params || !out || !dx) { ctx->err = "analyze_and_solve: null pointer"; return DCREG_BAD_ARG; }
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync(ctx->d_small, H27, 27 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    k2_analyze_kernel<<<1, 32, 0, ctx->stream>>>(ctx->d_small, *params, ctx->d_analysis, ctx->d_small + 32);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, ctx->d_analysis, sizeof(dcreg_analysis), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(dx, ctx->d_small + 32, 6 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < 6; ++i)
+        if (!isfinite(dx[i])) return DCREG_NONFINITE_UPDATE;
+    return DCREG_OK;
+}
+
+int dcreg_solve_pcg(dcreg_ctx* ctx, const double A[36], const double b[6], const double P[36], int max_iterations,
+                    double tolerance, double x[6], int* iterations) {
+    if (!ctx) return DCREG_BAD_ARG;
+    if (!A || !b || !P || !x) { ctx->err = "solve_pcg: null pointer"; return DCREG_BAD_ARG; }
+    CK(cudaSetDevice(ctx->device));
+    double* d = ctx->d_small;
+    CK(cudaMemcpyAsync(d, A, 36 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d + 36, b, 6 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d + 48, P, 36 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    pcg_kernel<<<1, 32, 0, ctx->stream>>>(d, d + 36, d + 48, max_iterations, tolerance, d + 96, (int*)(d + 128));
+    ctx->launches++;
+    CK(cudaGetLastError());
+    int it = 0;
+    CK(cudaMemcpyAsync(x, d + 96, 6 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(&it, d + 128, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (iterations) *iterations = it;
+    return DCREG_OK;
+}
+
+int dcreg_icp_run(dcreg_ctx* ctx, const dcreg_icp_params* params, const double T_init[16], double T_out[16],
+                  dcreg_iter_log* log, int log_cap, int* n_iterations, int* converged) {
+    if (!ctx) return DCREG_BAD_ARG;
+    if (!params || !T_init || !T_out) { ctx->err = "icp_run: null pointer"; return DCREG_BAD_ARG; }
+    if (!ctx->d_src || ctx->n_src <= 0) { ctx->err = "[ICP Error] Input measure cloud is null or empty."; return DCREG_BAD_ARG; }
+    if (!ctx->has_grid) { ctx->err = "[ICP Error] Target index is not set up in context."; return DCREG_BAD_ARG; }
+    if (params->max_iterations < 0) { ctx->err = "icp_run: max_iterations < 0"; return DCREG_BAD_ARG; }
+    CK(cudaSetDevice(ctx->device));
+    int rc;
+    if (log && log_cap > 0 && (rc = ensure_log(ctx, log_cap))) return rc;
+    dcreg_iter_log* dlog = (log && log_cap > 0) ? ctx->d_log : nullptr;
+    if ((rc = init_state(ctx, T_init))) return rc;
+    int issued = 0;
+    int chunk = 16;
+    int status = DCREG_OK;
+    int rc2 = ensure_pinned(ctx, sizeof(IcpState));
+    if (rc2) return rc2;
+    while (issued < params->max_iterations) {
+        const int todo = (params->max_iterations - issued) < chunk ? (params->max_iterations - issued) : chunk;
+        for (int k = 0; k < todo; ++k) {
+            if ((rc = launch_iteration(ctx, params, nullptr))) return rc;
+            if ((rc = nccl_allreduce_acc(ctx))) return rc;          // no-op on one GPU
+            k2_step_kernel<<<1, 32, 0, ctx->stream>>>(ctx->d_acc, ctx->d_state, *params, dlog, log_cap);
+            ctx->launches++;
+        }
+        issued += todo;
+        if (issued < params->max_iterations && !params->fixed_iterations) {
+            // peek at the done flag between chunks (the only host sync inside a run)
+            int* flag = (int*)ctx->h_pinned;
+            CK(cudaMemcpyAsync(flag, &ctx->d_state->done, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            if (*flag) break;
+            chunk = 32;
+        }
+    }
+    if ((rc = read_results(ctx, T_out, log, log_cap, n_iterations, converged, &status))) return rc;
+    return status;
+}
+
+int dcreg_icp_run_host_planes(dcreg_ctx* ctx, const dcreg_icp_params* params, const double T_init[16],
+                              dcreg_plane_callback cb, void* user, double T_out[16], dcreg_iter_log* log,
+                              int log_cap, int* n_iterations, int* converged) {
+    if (!ctx) return DCREG_BAD_ARG;
+    if (!params || !T_init || !T_out || !cb) { ctx->err = "icp_run_host_planes: null pointer"; return DCREG_BAD_ARG; }
+    if (!ctx->d_src || ctx->n_src <= 0) { ctx->err = "[ICP Error] Input measure cloud is null or empty."; return DCREG_BAD_ARG; }
+    CK(cudaSetDevice(ctx->device));
+    int rc;
+    if (log && log_cap > 0 && (rc = ensure_log(ctx, log_cap))) return rc;
+    dcreg_iter_log* dlog = (log && log_cap > 0) ? ctx->d_log : nullptr;
+    if ((rc = ensure_planes(ctx, ctx->n_src))) return rc;
+    if ((rc = ensure_pinned(ctx, sizeof(IcpState) + (size_t)ctx->n_src * sizeof(double4)))) return rc;
+    IcpState* hs = (IcpState*)ctx->h_pinned;
+    double* hplanes = (double*)((char*)ctx->h_pinned + sizeof(IcpState));
+    if ((rc = init_state(ctx, T_init))) return rc;
+    double T[16];
+    memcpy(T, T_init, sizeof(T));
+    for (int it = 0; it < params->max_iterations; ++it) {
+        int64_t npt = 0;
+        if (cb(user, T, hplanes, &npt) != 0) { ctx->err = "plane callback failed"; return DCREG_BAD_ARG; }
+        CK(cudaMemcpyAsync(ctx->d_planes64, hplanes, (size_t)ctx->n_src * sizeof(double4), cudaMemcpyHostToDevice,
+                           ctx->stream));
+        if ((rc = launch_reduce(ctx, ctx->d_src, ctx->d_planes64, true, ctx->n_src, nullptr,
+                                params->use_weight_derivative, ctx->d_state)))
+            return rc;
+        if ((rc = nccl_allreduce_acc(ctx))) return rc;
+        k2_step_kernel<<<1, 32, 0, ctx->stream>>>(ctx->d_acc, ctx->d_state, *params, dlog, log_cap);
+        ctx->launches++;
+        CK(cudaMemcpyAsync(hs, ctx->d_state, sizeof(IcpState), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        for (int r = 0; r < 3; ++r) {
+            for (int c = 0; c < 3; ++c) T[r * 4 + c] = hs->R[r * 3 + c];
+            T[r * 4 + 3] = hs->t[r];
+        }
+        if (hs->done) break;
+    }
+    int status = DCREG_OK;
+    if ((rc = read_results(ctx, T_out, log, log_cap, n_iterations, converged, &status))) return rc;
+    return status;
+}
+
+int dcreg_last_covariance(dcreg_ctx* ctx, double cov[36]) {
+    if (!ctx || !cov) return DCREG_BAD_ARG;
+    CK(cudaSetDevice(ctx->device));
+    covariance_kernel<<<1, 32, 0, ctx->stream>>>(ctx->d_state, ctx->d_small + 256);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(cov, ctx->d_small + 256, 36 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return DCREG_OK;
+}
+
+int dcreg_comm_unique_id(dcreg_ctx* ctx, uint8_t id_out[128]) {
+    if (!ctx || !id_out) return DCREG_BAD_ARG;
+    if (!g_nccl.load(ctx->err)) return DCREG_NCCL_ERROR;
+    ncclUniqueId id;
+    int r = g_nccl.GetUniqueId(&id);
+    if (r != 0) { ctx->err = "ncclGetUniqueId failed"; return DCREG_NCCL_ERROR; }
+    memcpy(id_out, id.internal, 128);
+    return DCREG_OK;
+}
+
+int dcreg_comm_init(dcreg_ctx* ctx, const uint8_t nccl_unique_id[128], int rank, int nranks) {
+    if (!ctx || !nccl_unique_id || nranks < 1 || rank < 0 || rank >= nranks) return DCREG_BAD_ARG;
+    if (!g_nccl.load(ctx->err)) return DCREG_NCCL_ERROR;
+    CK(cudaSetDevice(ctx->device));
+    ncclUniqueId id;
+    memcpy(id.internal, nccl_unique_id, 128);
+    int r = g_nccl.CommInitRank(&ctx->comm, nranks, id, rank);
+    if (r != 0) {
+        ctx->comm = nullptr;
+        ctx->err = std::string("ncclCommInitRank: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error");
+        return DCREG_NCCL_ERROR;
+    }
+    ctx->rank = rank; ctx->nranks = nranks;
+    return DCREG_OK;
+}
+
+int dcreg_comm_destroy(dcreg_ctx* ctx) {
+    if (!ctx) return DCREG_BAD_ARG;
+    if (ctx->comm && g_nccl.CommDestroy) {
+        cudaStreamSynchronize(ctx->stream);
+        g_nccl.CommDestroy(ctx->comm);
+    }
+    ctx->comm = nullptr; ctx->rank = 0; ctx->nranks = 1;
+    return DCREG_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,397 @@
+// k2_solve.cuh - K2: degeneracy analysis + solve + SE(3) update, device side.
+//
+// What it replaces (reference file:line, relative to the DCReg checkout):
+//   DCReg::analyzeDegeneracy            DCReg/include/dcreg.hpp:45-166
+//   released Schur-complement block     DCReg/src/icp_test_runner.cpp:2418-2469
+//   Schur detection / preconditioner /  stubs at dcreg.hpp:96-98,186-193,267-287; algorithm from the
+//   PCG ("Ours")                        paper's Alg. 1-3, Eq. 18-21, 43-46
+//   DCReg::solveDegenerateSystem        dcreg.hpp:168-264 (TReg / SR / TSVD / QR handlers)
+//   SE3State::boxplus, MathUtils::exp   DCReg/include/math_utils.hpp:158-166, 20-33
+//   convergence / abort rules           icp_test_runner.cpp:1847-1854, 1942-1950, 1958-2003
+#pragma once
+#include "../../include/dcreg_b200.h"
+#include "small_la.cuh"
+
+namespace k2 {
+
+// accumulator layout shared by K1 and K2 (hessian_computer.h:62-123 order + stats)
+constexpr int kAcc = 32;        // 21 upper-tri + 6 rhs + sum r^2 + N_eff + N_corr_pt + sum b^2 (+1 pad)
+constexpr int kAccUsed = 31;
+constexpr int kAccSumR2 = 27;
+constexpr int kAccNeff = 28;
+constexpr int kAccNpt = 29;
+constexpr int kAccSumB2 = 30;
+
+struct IcpState {               // device-resident loop state, written only by K2
+    double R[9];
+    double t[3];
+    int iter;                   // iterations completed
+    int done;                   // 1: stop (converged, aborted or max_iterations reached)
+    int converged;
+    int status;                 // dcreg_status
+    double H_last[36];
+    long long n_source_total;   // denominator of fitness (global count when sharded)
+};
+
+__device__ inline void unpack_H(const double* v27, double* H, double* g) {
+    int k = 0;
+    for (int i = 0; i < 6; ++i)
+        for (int j = i; j < 6; ++j) { H[i * 6 + j] = v27[k]; H[j * 6 + i] = v27[k]; ++k; }
+    for (int i = 0; i < 6; ++i) g[i] = v27[21 + i];
+}
+
+__device__ inline double cond3(const double* lam) {   // lambda ascending
+    return lam[2] / fmax(lam[0], 1e-12);               // icp_test_runner.cpp:2454-2457
+}
+
+// paper Alg. 2 (log only): greedy assignment of eigenvectors to the reference axes, sign fix,
+// Gram-Schmidt in slot order.  indices[j] = column of V_raw that landed in slot j.
+__device__ inline void align_axes(const double* V, double* Va, int* indices) {
+    bool used_v[3] = {false, false, false}, used_e[3] = {false, false, false};
+    for (int round = 0; round < 3; ++round) {
+        double best = -1.0; int bi = 0, bj = 0;
+        for (int j = 0; j < 3; ++j) {
+            if (used_e[j]) continue;
+            for (int i = 0; i < 3; ++i) {
+                if (used_v[i]) continue;
+                const double a = fabs(V[j * 3 + i]);     // |v_i . e_j| = |V[j][i]|
+                if (a > best) { best = a; bi = i; bj = j; }
+            }
+        }
+        used_v[bi] = true; used_e[bj] = true; indices[bj] = bi;
+    }
+    for (int j = 0; j < 3; ++j) {
+        double v[3] = {V[0 * 3 + indices[j]], V[1 * 3 + indices[j]], V[2 * 3 + indices[j]]};
+        if (v[j] < 0.0) { v[0] = -v[0]; v[1] = -v[1]; v[2] = -v[2]; }
+        for (int k = 0; k < j; ++k) {
+            const double d = v[0] * Va[0 * 3 + k] + v[1] * Va[1 * 3 + k] + v[2] * Va[2 * 3 + k];
+            v[0] -= d * Va[0 * 3 + k]; v[1] -= d * Va[1 * 3 + k]; v[2] -= d * Va[2 * 3 + k];
+        }
+        const double nrm = sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+        const double inv = nrm > 0.0 ? 1.0 / nrm : 0.0;
+        Va[0 * 3 + j] = v[0] * inv; Va[1 * 3 + j] = v[1] * inv; Va[2 * 3 + j] = v[2] * inv;
+    }
+}
+
+// PCG on H x = g, x0 = 0 (paper Alg. 3; stub DCReg::solvePCG dcreg.hpp:279-287).
+// Stops when ||r||_2 < tol or after max_iter iterations.  Returns iterations used.
+__device__ inline int pcg6(const double* H, const double* g, const double* P, int max_iter,
+                           double tol, double* x, double* res_out) {
+    double r[6], z[6], p[6], Hp[6];
+    for (int i = 0; i < 6; ++i) { x[i] = 0.0; r[i] = g[i]; }
+    dla::mat6_vec(P, r, z);
+    double rz = 0.0;
+    for (int i = 0; i < 6; ++i) { p[i] = z[i]; rz += r[i] * z[i]; }
+    int it = 0;
+    double rn = 0.0;
+    for (int i = 0; i < 6; ++i) rn += r[i] * r[i];
+    rn = sqrt(rn);
+    for (it = 1; it <= max_iter; ++it) {
+        dla::mat6_vec(H, p, Hp);
+        double pHp = 0.0;
+        for (int i = 0; i < 6; ++i) pHp += p[i] * Hp[i];
+        const double alpha = rz / pHp;
+        rn = 0.0;
+        for (int i = 0; i < 6; ++i) { x[i] += alpha * p[i]; r[i] -= alpha * Hp[i]; rn += r[i] * r[i]; }
+        rn = sqrt(rn);
+        if (rn < tol) break;
+        dla::mat6_vec(P, r, z);
+        double rz_new = 0.0;
+        for (int i = 0; i < 6; ++i) rz_new += r[i] * z[i];
+        const double beta = rz_new / rz;
+        for (int i = 0; i < 6; ++i) p[i] = z[i] + beta * p[i];
+        rz = rz_new;
+    }
+    if (it > max_iter) it = max_iter;
+    *res_out = rn;
+    return it;
+}
+
+__device__ inline void qr6(const double* H, const double* g, double* x) {
+    double A[36], b[6];
+    for (int i = 0; i < 36; ++i) A[i] = H[i];
+    for (int i = 0; i < 6; ++i) b[i] = g[i];
+    dla::colpiv_qr_solve<6, 6>(A, b, x);
+}
+
+// analysis + solve for one 6x6 system.  Single thread.
+__device__ inline void analyze_and_solve(const double* v27, const dcreg_icp_params& prm,
+                                         dcreg_analysis* a, double* dx) {
+    double H[36], g[6];
+    unpack_H(v27, H, g);
+    const double NaN = nan("");
+
+    // ---- defaults of DegeneracyAnalysisResult (utils.hpp:427-448) ----
+    a->is_degenerate = 0; a->pcg_iterations = 0; a->pcg_residual = 0.0;
+    for (int i = 0; i < 6; ++i) a->degenerate_mask[i] = 0;
+    for (int i = 0; i < 36; ++i) a->P_preconditioner[i] = (i % 7 == 0) ? 1.0 : 0.0;
+    for (int i = 0; i < 9; ++i) {
+        const double e = (i % 4 == 0) ? 1.0 : 0.0;
+        a->aligned_V_rot[i] = a->aligned_V_trans[i] = a->schur_V_rot[i] = a->schur_V_trans[i] = e;
+    }
+    for (int i = 0; i < 3; ++i) { a->rot_indices[i] = a->trans_indices[i] = i; }
+    a->reserved1[0] = a->reserved1[1] = 0;
+
+    // ---- full EVD / "SVD" of H (dcreg.hpp:62-89) ----
+    double W[36], lam[6], V[36];
+    for (int i = 0; i < 36; ++i) W[i] = H[i];
+    dla::jacobi_eigh<6>(W, lam, V);
+    for (int i = 0; i < 6; ++i) a->eigenvalues_full[i] = lam[i];
+    a->cond_full_sub_trans = fabs(lam[2]) / fmax(fabs(lam[0]), 1e-12);
+    a->cond_full_sub_rot = fabs(lam[5]) / fmax(fabs(lam[3]), 1e-12);
+    // singular values of a symmetric matrix = |eigenvalues|, descending; order[] maps
+    // singular index -> eigen index (needed by the TSVD handler)
+    int order[6];
+    for (int i = 0; i < 6; ++i) order[i] = i;
+    for (int i = 0; i < 5; ++i) {
+        int m = i;
+        for (int j = i + 1; j < 6; ++j)
+            if (fabs(lam[order[j]]) > fabs(lam[order[m]])) m = j;
+        const int t = order[i]; order[i] = order[m]; order[m] = t;
+    }
+    for (int i = 0; i < 6; ++i) a->singular_values[i] = fabs(lam[order[i]]);
+    a->cond_full = (a->singular_values[5] > 1e-12) ? a->singular_values[0] / a->singular_values[5]
+                                                   : (double)INFINITY;
+
+    // ---- diagonal blocks + Schur complements (icp_test_runner.cpp:2418-2469, paper Eq. 18) ----
+    double HRR[9], Htt[9], HRt[9], HtR[9];
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) {
+            HRR[i * 3 + j] = H[i * 6 + j];
+            Htt[i * 3 + j] = H[(i + 3) * 6 + j + 3];
+            HRt[i * 3 + j] = H[i * 6 + j + 3];
+            HtR[i * 3 + j] = H[(i + 3) * 6 + j];
+        }
+    double tmpA[9], tmpV[9];
+    for (int i = 0; i < 9; ++i) tmpA[i] = HRR[i];
+    dla::jacobi_eigh<3>(tmpA, a->lambda_sub_rot, tmpV);
+    for (int i = 0; i < 9; ++i) tmpA[i] = Htt[i];
+    dla::jacobi_eigh<3>(tmpA, a->lambda_sub_trans, tmpV);
+    a->cond_diag_rot = cond3(a->lambda_sub_rot);
+    a->cond_diag_trans = cond3(a->lambda_sub_trans);
+
+    double HttInv[9], HRRInv[9];
+    for (int i = 0; i < 9; ++i) tmpA[i] = Htt[i];
+    const bool ok_t = dla::fullpiv_inverse<3>(tmpA, HttInv);
+    for (int i = 0; i < 9; ++i) tmpA[i] = HRR[i];
+    const bool ok_r = dla::fullpiv_inverse<3>(tmpA, HRRInv);
+    bool schur_ok = ok_t && ok_r;
+    if (schur_ok) {
+        double T1[9], T2[9], SR[9], St[9];
+        dla::mat3_mul(HRt, HttInv, T1); dla::mat3_mul(T1, HtR, T2);
+        for (int i = 0; i < 9; ++i) SR[i] = HRR[i] - T2[i];
+        dla::mat3_mul(HtR, HRRInv, T1); dla::mat3_mul(T1, HRt, T2);
+        for (int i = 0; i < 9; ++i) St[i] = Htt[i] - T2[i];
+        // SelfAdjointEigenSolver reads one triangle only; symmetrise so Jacobi sees the same matrix
+        for (int i = 0; i < 3; ++i)
+            for (int j = i + 1; j < 3; ++j) {
+                const double m1 = 0.5 * (SR[i * 3 + j] + SR[j * 3 + i]); SR[i * 3 + j] = SR[j * 3 + i] = m1;
+                const double m2 = 0.5 * (St[i * 3 + j] + St[j * 3 + i]); St[i * 3 + j] = St[j * 3 + i] = m2;
+            }
+        dla::jacobi_eigh<3>(SR, a->lambda_schur_rot, a->schur_V_rot);
+        dla::jacobi_eigh<3>(St, a->lambda_schur_trans, a->schur_V_trans);
+        a->cond_schur_rot = cond3(a->lambda_schur_rot);
+        a->cond_schur_trans = cond3(a->lambda_schur_trans);
+        align_axes(a->schur_V_rot, a->aligned_V_rot, a->rot_indices);
+        align_axes(a->schur_V_trans, a->aligned_V_trans, a->trans_indices);
+    } else {
+        for (int i = 0; i < 3; ++i) a->lambda_schur_rot[i] = a->lambda_schur_trans[i] = NaN;
+        a->cond_schur_rot = a->cond_schur_trans = (double)INFINITY;
+    }
+
+    // ---- detection (dcreg.hpp:94-162 + paper Eq. 20-21 for the Schur case) ----
+    switch (prm.detection) {
+        case DCREG_DET_SCHUR_CONDITION_NUMBER:
+            if (schur_ok) {
+                for (int blk = 0; blk < 2; ++blk) {
+                    const double* l = blk ? a->lambda_schur_trans : a->lambda_schur_rot;
+                    const double* Vb = blk ? a->schur_V_trans : a->schur_V_rot;
+                    double lt[3];
+                    for (int i = 0; i < 3; ++i) {
+                        if (l[2] / fmax(l[i], 1e-12) > prm.cond_thresh) {
+                            a->degenerate_mask[blk * 3 + i] = 1; a->is_degenerate = 1;
+                        }
+                        lt[i] = fmax(l[i], l[2] / prm.kappa_target);     // Eq. 46
+                    }
+                    for (int i = 0; i < 3; ++i)
+                        for (int j = 0; j < 3; ++j) {
+                            double s = 0.0;
+                            for (int k = 0; k < 3; ++k) s += Vb[i * 3 + k] * Vb[j * 3 + k] / lt[k];
+                            a->P_preconditioner[(blk * 3 + i) * 6 + blk * 3 + j] = s;   // Eq. 43-44
+                        }
+                }
+            }
+            break;
+        case DCREG_DET_FULL_EVD_MIN_EIGENVALUE:
+            for (int i = 0; i < 6; ++i)
+                if (lam[i] < prm.eig_thresh) { a->is_degenerate = 1; a->degenerate_mask[i] = 1; }
+            break;
+        case DCREG_DET_EVD_SUB_CONDITION:
+            // dcreg.hpp:112-126 tests cond_diag_* which the released analyzeDegeneracy leaves NaN:
+            // the comparison is always false.  Kept as released.
+            break;
+        case DCREG_DET_FULL_SVD_CONDITION:
+            a->is_degenerate = (a->cond_full > prm.cond_thresh) ? 1 : 0;
+            if (a->is_degenerate) {
+                const double mx = lam[5];
+                for (int i = 0; i < 6; ++i)
+                    if (mx / lam[i] > prm.cond_thresh) a->degenerate_mask[i] = 1;
+            }
+            break;
+        default: break;
+    }
+
+    // ---- handling (dcreg.hpp:168-264) ----
+    switch (prm.handling) {
+        case DCREG_HAND_STANDARD_REGULARIZATION: {
+            double Hr[36];
+            for (int i = 0; i < 36; ++i) Hr[i] = H[i];
+            if (a->is_degenerate) for (int i = 0; i < 6; ++i) Hr[i * 7] += prm.std_reg_gamma;
+            qr6(Hr, g, dx);
+            break;
+        }
+        case DCREG_HAND_PRECONDITIONED_CG:
+            if (a->is_degenerate) {
+                a->pcg_iterations = pcg6(H, g, a->P_preconditioner, prm.pcg_max_iter, prm.pcg_tol, dx,
+                                         &a->pcg_residual);
+            } else {
+                qr6(H, g, dx);
+            }
+            break;
+        case DCREG_HAND_SOLUTION_REMAPPING: {
+            double x0[6];
+            qr6(H, g, x0);
+            if (a->is_degenerate) {
+                int good = 0;
+                for (int i = 0; i < 6; ++i) dx[i] = 0.0;
+                for (int k = 0; k < 6; ++k) {
+                    if (a->degenerate_mask[k]) continue;
+                    ++good;
+                    double d = 0.0;
+                    for (int i = 0; i < 6; ++i) d += V[i * 6 + k] * x0[i];
+                    for (int i = 0; i < 6; ++i) dx[i] += V[i * 6 + k] * d;
+                }
+                if (good == 0) for (int i = 0; i < 6; ++i) dx[i] = 0.0;
+            } else {
+                for (int i = 0; i < 6; ++i) dx[i] = x0[i];
+            }
+            break;
+        }
+        case DCREG_HAND_TRUNCATED_SVD: {
+            // mask[i] (ascending-eigenvalue index) is paired with sigma_i (descending) exactly as
+            // the reference does (dcreg.hpp:232-237) - a quirk of the baseline, kept.
+            int kept = 0;
+            for (int i = 0; i < 6; ++i) dx[i] = 0.0;
+            for (int i = 0; i < 6; ++i) {
+                const double sig = a->singular_values[i];
+                if (!a->degenerate_mask[i] && sig > 1e-9) {
+                    ++kept;
+                    const int e = order[i];
+                    double d = 0.0;
+                    for (int r = 0; r < 6; ++r) d += V[r * 6 + e] * g[r];
+                    const double sc = (lam[e] >= 0.0 ? 1.0 : -1.0) * d / sig;
+                    for (int r = 0; r < 6; ++r) dx[r] += V[r * 6 + e] * sc;
+                }
+            }
+            if (kept == 0) for (int i = 0; i < 6; ++i) dx[i] = 0.0;
+            break;
+        }
+        default:
+            qr6(H, g, dx);
+            break;
+    }
+}
+
+// R <- R exp(w), t <- t + R_old v  (math_utils.hpp:158-166, 20-33)
+__device__ inline void boxplus(double* R, double* t, const double* dx) {
+    const double wx = dx[0], wy = dx[1], wz = dx[2];
+    const double theta = sqrt(wx * wx + wy * wy + wz * wz);
+    double E[9];
+    if (theta < 1e-10) {
+        E[0] = 1.0; E[1] = -wz; E[2] = wy;
+        E[3] = wz;  E[4] = 1.0; E[5] = -wx;
+        E[6] = -wy; E[7] = wx;  E[8] = 1.0;
+    } else {
+        const double ax = wx / theta, ay = wy / theta, az = wz / theta;
+        const double K[9] = {0.0, -az, ay, az, 0.0, -ax, -ay, ax, 0.0};
+        double K2[9];
+        dla::mat3_mul(K, K, K2);
+        const double s = sin(theta), c1 = 1.0 - cos(theta);
+        for (int i = 0; i < 9; ++i) E[i] = ((i % 4 == 0) ? 1.0 : 0.0) + s * K[i] + c1 * K2[i];
+    }
+    double Rn[9];
+    dla::mat3_mul(R, E, Rn);
+    const double v0 = dx[3], v1 = dx[4], v2 = dx[5];
+    t[0] += R[0] * v0 + R[1] * v1 + R[2] * v2;
+    t[1] += R[3] * v0 + R[4] * v1 + R[5] * v2;
+    t[2] += R[6] * v0 + R[7] * v1 + R[8] * v2;
+    for (int i = 0; i < 9; ++i) R[i] = Rn[i];
+}
+
+// One full K2 step on the reduced accumulators: abort rules, analysis, solve, pose update,
+// convergence flag and log record.  Single thread.
+__device__ inline void icp_step(const double* acc, IcpState* st, const dcreg_icp_params& prm,
+                                dcreg_iter_log* log, int log_cap) {
+    const int iter = st->iter;
+    dcreg_iter_log* rec = (log != nullptr && iter < log_cap) ? &log[iter] : nullptr;
+    dcreg_analysis scratch;
+    dcreg_analysis* an = rec ? &rec->analysis : &scratch;
+    const int n_eff = (int)(acc[kAccNeff] + 0.5);
+    const int n_pt = (int)(acc[kAccNpt] + 0.5);
+    if (rec) {
+        rec->iter = iter; rec->n_effective = n_eff; rec->n_corr_pt = n_pt; rec->status = DCREG_OK;
+        for (int i = 0; i < 27; ++i) rec->H27[i] = acc[i];
+    }
+    if (n_eff < prm.min_effective_points) {                 // icp_test_runner.cpp:1847-1854
+        st->iter = iter + 1; st->done = 1; st->converged = 0; st->status = DCREG_NOT_ENOUGH_POINTS;
+        if (rec) {
+            rec->status = DCREG_NOT_ENOUGH_POINTS; rec->rmse = 0.0; rec->fitness = 0.0; rec->objective = 0.0;
+            for (int i = 0; i < 6; ++i) { rec->gradient[i] = 0.0; rec->dx[i] = 0.0; }
+            for (int r = 0; r < 3; ++r) {
+                for (int c = 0; c < 3; ++c) rec->T[r * 4 + c] = st->R[r * 3 + c];
+                rec->T[r * 4 + 3] = st->t[r];
+            }
+            rec->T[12] = rec->T[13] = rec->T[14] = 0.0; rec->T[15] = 1.0;
+        }
+        return;
+    }
+    double dx[6];
+    analyze_and_solve(acc, prm, an, dx);
+    bool finite = true;
+    for (int i = 0; i < 6; ++i) finite = finite && isfinite(dx[i]);
+    const double fitness = st->n_source_total > 0 ? (double)n_pt / (double)st->n_source_total : 0.0;
+    const double rmse = sqrt(acc[kAccSumR2] / (double)n_eff);
+    if (rec) {
+        rec->rmse = rmse; rec->fitness = fitness;
+        for (int i = 0; i < 6; ++i) rec->gradient[i] = -acc[21 + i];
+    }
+    if (!finite) {                                          // icp_test_runner.cpp:1942-1950
+        st->done = 1; st->converged = 0; st->status = DCREG_NONFINITE_UPDATE;
+        if (rec) { rec->status = DCREG_NONFINITE_UPDATE; for (int i = 0; i < 6; ++i) rec->dx[i] = 0.0; }
+        return;
+    }
+    boxplus(st->R, st->t, dx);                              // icp_test_runner.cpp:1953
+    {
+        double gtmp[6];
+        unpack_H(acc, st->H_last, gtmp);                    // matAtA_last, icp_test_runner.cpp:1965
+    }
+    if (rec) {
+        rec->objective = 0.5 * acc[kAccSumB2];              // icp_test_runner.cpp:1919
+        for (int i = 0; i < 6; ++i) rec->dx[i] = dx[i];
+        for (int r = 0; r < 3; ++r) {
+            for (int c = 0; c < 3; ++c) rec->T[r * 4 + c] = st->R[r * 3 + c];
+            rec->T[r * 4 + 3] = st->t[r];
+        }
+        rec->T[12] = rec->T[13] = rec->T[14] = 0.0; rec->T[15] = 1.0;
+    }
+    const double dR = sqrt(dx[0] * dx[0] + dx[1] * dx[1] + dx[2] * dx[2]);
+    const double dT = sqrt(dx[3] * dx[3] + dx[4] * dx[4] + dx[5] * dx[5]);
+    st->iter = iter + 1;
+    if (!prm.fixed_iterations && dR < prm.conv_thresh_rot && dT < prm.conv_thresh_trans) {
+        st->converged = 1; st->done = 1;                    // icp_test_runner.cpp:1998-2002
+    } else if (st->iter >= prm.max_iterations) {
+        st->done = 1;
+    }
+}
+
+}  // namespace k2
