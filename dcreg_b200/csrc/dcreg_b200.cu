@@ -15,6 +15,7 @@
 #include <math.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -23,6 +24,7 @@
 #include "../../include/dcreg_b200.h"
 #include "corr.cuh"
 #include "k1_reduce.cuh"
+#include "k1_mma.cuh"
 #include "k2_solve.cuh"
 
 using k2::IcpState;
@@ -97,86 +99,6 @@ __global__ void __launch_bounds__(kBlock) icp_iteration_kernel(IterArgs a) {
         }
         if (a.planes_out) a.planes_out[i] = ok ? make_double4(nx, ny, nz, d) : make_double4(0.0, 0.0, 0.0, 0.0);
         k1::accumulate_slot(acc, P, px, py, pz, nx, ny, nz, d, use_wd, ok);
-    }
-    k1::block_reduce_store(acc, smem, a.partials + (size_t)blockIdx.x * kAcc);
-    if (last_block_ticket(a.counter)) {
-        __syncthreads();
-        k1::final_reduce(a.partials, gridDim.x, P.R, smem, a.acc);
-        if (threadIdx.x == 0) *a.counter = 0u;
-    }
-}
-
-// K1 standalone: frozen planes (float4 = 32 B/slot, double4 = 48 B/slot).
-template <typename PlaneT>
-struct PlaneLoad;
-template <>
-struct PlaneLoad<float4> {
-    static __device__ __forceinline__ void get(const float4* p, long long i, double& nx, double& ny, double& nz,
-                                               double& d, bool& has) {
-        const float4 v = __ldg(&p[i]);
-        has = (v.x != 0.0f) || (v.y != 0.0f) || (v.z != 0.0f);
-        nx = (double)v.x; ny = (double)v.y; nz = (double)v.z; d = (double)v.w;
-    }
-};
-template <>
-struct PlaneLoad<double4> {
-    static __device__ __forceinline__ void get(const double4* p, long long i, double& nx, double& ny, double& nz,
-                                               double& d, bool& has) {
-        const double2 a = __ldg(reinterpret_cast<const double2*>(p) + 2 * i);
-        const double2 b = __ldg(reinterpret_cast<const double2*>(p) + 2 * i + 1);
-        has = (a.x != 0.0) || (a.y != 0.0) || (b.x != 0.0);
-        nx = a.x; ny = a.y; nz = b.x; d = b.y;
-    }
-};
-
-struct ReduceArgs {
-    const float4* src;
-    const void* plane;
-    long long n;
-    k1::Pose pose;
-    int use_wd;
-    double* partials;
-    unsigned int* counter;
-    double* acc;
-    IcpState* state;          // when non-null: pose is read from state (ICP loop, host-plane mode)
-};
-
-constexpr int kK1Unroll = 4;
-
-template <typename PlaneT>
-__global__ void __launch_bounds__(kBlock) reduce_kernel(ReduceArgs a) {
-    __shared__ double smem[(kBlock / 32) * kAcc];
-    if (a.state && a.state->done) return;
-    const k1::Pose P = a.state ? load_pose(a.state) : a.pose;
-    const PlaneT* plane = reinterpret_cast<const PlaneT*>(a.plane);
-    k1::Acc acc;
-    k1::acc_zero(acc);
-    const bool use_wd = a.use_wd != 0;
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    // main loop: kK1Unroll independent slots per thread, all loads issued before the FP64 work
-    for (; i + (kK1Unroll - 1) * stride < a.n; i += kK1Unroll * stride) {
-        float4 p4[kK1Unroll];
-        double nx[kK1Unroll], ny[kK1Unroll], nz[kK1Unroll], d[kK1Unroll];
-        bool has[kK1Unroll];
-#pragma unroll
-        for (int u = 0; u < kK1Unroll; ++u) p4[u] = __ldg(&a.src[i + u * stride]);
-#pragma unroll
-        for (int u = 0; u < kK1Unroll; ++u) PlaneLoad<PlaneT>::get(plane, i + u * stride, nx[u], ny[u], nz[u], d[u], has[u]);
-#pragma unroll
-        for (int u = 0; u < kK1Unroll; ++u) {
-            acc.npt += has[u] ? 1 : 0;
-            k1::accumulate_slot(acc, P, (double)p4[u].x, (double)p4[u].y, (double)p4[u].z, nx[u], ny[u], nz[u],
-                                d[u], use_wd, has[u]);
-        }
-    }
-    for (; i < a.n; i += stride) {
-        const float4 p4 = __ldg(&a.src[i]);
-        double nx, ny, nz, d;
-        bool has;
-        PlaneLoad<PlaneT>::get(plane, i, nx, ny, nz, d, has);
-        acc.npt += has ? 1 : 0;
-        k1::accumulate_slot(acc, P, (double)p4.x, (double)p4.y, (double)p4.z, nx, ny, nz, d, use_wd, has);
     }
     k1::block_reduce_store(acc, smem, a.partials + (size_t)blockIdx.x * kAcc);
     if (last_block_ticket(a.counter)) {
@@ -359,7 +281,7 @@ int ensure_partials(dcreg_ctx* ctx, int blocks) {
     if (ctx->partials_blocks >= blocks) return DCREG_OK;
     if (ctx->d_partials) cudaFree(ctx->d_partials);
     ctx->d_partials = nullptr;
-    CK(cudaMalloc(&ctx->d_partials, (size_t)blocks * kAcc * sizeof(double)));
+    CK(cudaMalloc(&ctx->d_partials, (size_t)blocks * 72 * sizeof(double)));   // >= k1m::kPart and kAcc
     ctx->partials_blocks = blocks;
     return DCREG_OK;
 }
@@ -407,21 +329,58 @@ int upload_points(dcreg_ctx* ctx, const float* xyz, long long n, int stride, flo
     return DCREG_OK;
 }
 
-int launch_reduce(dcreg_ctx* ctx, const float4* d_src, const void* d_plane, bool f64, long long n,
-                  const k1::Pose* pose, int use_wd, IcpState* state) {
-    const int grid = stream_grid(ctx, (n + kK1Unroll - 1) / kK1Unroll, 8);
-    int rc = ensure_partials(ctx, grid);
+template <typename PlaneT, bool kUseWd, int kMinBlocks, bool kDmma>
+int launch_reduce_t(dcreg_ctx* ctx, k1m::Args& a) {
+    auto kern = k1m::reduce_mma_kernel<PlaneT, kUseWd, kMinBlocks, kDmma>;
+    const size_t smem = sizeof(k1m::Smem<PlaneT>);
+    static int blocks_per_sm = 0;
+    if (blocks_per_sm == 0) {
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        int nb = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, k1m::kThreads, smem));
+        if (getenv("DCREG_K1_VERBOSE")) fprintf(stderr, "[dcreg] K1 smem %zu B/block, %d blocks/SM\n", smem, nb);
+        blocks_per_sm = nb > 0 ? nb : 1;
+    }
+    // persistent grid: every SM holds `blocks_per_sm` CTAs; warps take 32-slot chunks round-robin
+    const long long nchunks = (a.n + 31) / 32;
+    long long g = (long long)ctx->sm_count * blocks_per_sm;
+    const long long need = (nchunks + k1m::kWarpsPerBlock - 1) / k1m::kWarpsPerBlock;
+    if (g > need) g = need;
+    if (g < 1) g = 1;
+    int rc = ensure_partials(ctx, (int)g);
     if (rc) return rc;
-    ReduceArgs a{};
-    a.src = d_src; a.plane = d_plane; a.n = n;
-    if (pose) a.pose = *pose;
-    a.use_wd = use_wd; a.partials = ctx->d_partials; a.counter = ctx->d_counter; a.acc = ctx->d_acc;
-    a.state = state;
-    if (f64) reduce_kernel<double4><<<grid, kBlock, 0, ctx->stream>>>(a);
-    else reduce_kernel<float4><<<grid, kBlock, 0, ctx->stream>>>(a);
+    a.partials = ctx->d_partials;
+    kern<<<(int)g, k1m::kThreads, smem, ctx->stream>>>(a);
     ctx->launches++;
     CK(cudaGetLastError());
     return DCREG_OK;
+}
+
+template <int kMinBlocks, bool kDmma>
+int launch_reduce_v(dcreg_ctx* ctx, k1m::Args& a, bool f64, bool wd) {
+    if (wd) return f64 ? launch_reduce_t<double4, true, kMinBlocks, kDmma>(ctx, a) : launch_reduce_t<float4, true, kMinBlocks, kDmma>(ctx, a);
+    return f64 ? launch_reduce_t<double4, false, kMinBlocks, kDmma>(ctx, a) : launch_reduce_t<float4, false, kMinBlocks, kDmma>(ctx, a);
+}
+
+int k1_variant() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("DCREG_K1_VARIANT"); v = e ? atoi(e) : 0; }
+    return v;
+}
+
+int launch_reduce(dcreg_ctx* ctx, const float4* d_src, const void* d_plane, bool f64, long long n,
+                  const k1::Pose* pose, int use_wd) {
+    k1m::Args a{};
+    a.src = d_src; a.plane = d_plane; a.n = n;
+    if (pose) a.pose = *pose;
+    a.counter = ctx->d_counter; a.acc = ctx->d_acc;
+    switch (k1_variant()) {
+        case 1: return launch_reduce_v<1, false>(ctx, a, f64, use_wd != 0);
+        case 2: return launch_reduce_v<2, false>(ctx, a, f64, use_wd != 0);
+        case 4: return launch_reduce_v<4, true>(ctx, a, f64, use_wd != 0);
+        default: return launch_reduce_v<3, true>(ctx, a, f64, use_wd != 0);
+    }
 }
 
 int nccl_allreduce_acc(dcreg_ctx* ctx) {
@@ -658,7 +617,7 @@ static int reduce_common(dcreg_ctx* ctx, const void* d_src, const void* d_plane,
     k1::Pose P;
     for (int i = 0; i < 9; ++i) P.R[i] = pose_Rt[i];
     for (int i = 0; i < 3; ++i) P.t[i] = pose_Rt[9 + i];
-    int rc = launch_reduce(ctx, (const float4*)d_src, d_plane, f64, n, &P, use_wd, nullptr);
+    int rc = launch_reduce(ctx, (const float4*)d_src, d_plane, f64, n, &P, use_wd);
     if (rc) return rc;
     if ((rc = nccl_allreduce_acc(ctx))) return rc;
     double acc[kAcc];
@@ -721,27 +680,42 @@ int dcreg_time_reduce(dcreg_ctx* ctx, int plane_is_f64, const double pose_Rt[12]
         ctx->flush_n = (256ll << 20) / sizeof(float4);   // 256 MiB > 126 MB L2
         CK(cudaMalloc(&ctx->d_flush, (size_t)ctx->flush_n * sizeof(float4)));
     }
-    std::vector<cudaEvent_t> e0(reps), e1(reps);
-    for (int i = 0; i < reps; ++i) { CK(cudaEventCreate(&e0[i])); CK(cudaEventCreate(&e1[i])); }
     const void* plane = plane_is_f64 ? (const void*)ctx->d_planes64 : (const void*)ctx->d_planes32;
     int rc = DCREG_OK;
-    for (int i = 0; i < reps && rc == DCREG_OK; ++i) {
-        if (flush_l2) {
+    double total = 0.0;
+    if (!flush_l2) {
+        // one event pair around the whole batch of back-to-back launches (inputs larger than L2 need no flush)
+        cudaEvent_t b0, b1;
+        CK(cudaEventCreate(&b0)); CK(cudaEventCreate(&b1));
+        CK(cudaEventRecord(b0, ctx->stream));
+        for (int i = 0; i < reps && rc == DCREG_OK; ++i) {
+            rc = launch_reduce(ctx, ctx->d_src, plane, plane_is_f64 != 0, ctx->n_src, &P, use_weight_derivative);
+            if (rc == DCREG_OK) rc = nccl_allreduce_acc(ctx);      // sharded: the 32-double all-reduce is part of the step
+        }
+        CK(cudaEventRecord(b1, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, b0, b1);
+        total = ms;
+        cudaEventDestroy(b0); cudaEventDestroy(b1);
+    } else {
+        std::vector<cudaEvent_t> e0(reps), e1(reps);
+        for (int i = 0; i < reps; ++i) { CK(cudaEventCreate(&e0[i])); CK(cudaEventCreate(&e1[i])); }
+        for (int i = 0; i < reps && rc == DCREG_OK; ++i) {
             flush_l2_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(ctx->d_flush, ctx->flush_n, (float)i);
             ctx->launches++;
+            CK(cudaEventRecord(e0[i], ctx->stream));
+            rc = launch_reduce(ctx, ctx->d_src, plane, plane_is_f64 != 0, ctx->n_src, &P, use_weight_derivative);
+            if (rc == DCREG_OK) rc = nccl_allreduce_acc(ctx);
+            CK(cudaEventRecord(e1[i], ctx->stream));
         }
-        CK(cudaEventRecord(e0[i], ctx->stream));
-        rc = launch_reduce(ctx, ctx->d_src, plane, plane_is_f64 != 0, ctx->n_src, &P, use_weight_derivative, nullptr);
-        if (rc == DCREG_OK) rc = nccl_allreduce_acc(ctx);      // sharded: the 32-double all-reduce is part of the step
-        CK(cudaEventRecord(e1[i], ctx->stream));
-    }
-    CK(cudaStreamSynchronize(ctx->stream));
-    double total = 0.0;
-    for (int i = 0; i < reps; ++i) {
-        float ms = 0.f;
-        cudaEventElapsedTime(&ms, e0[i], e1[i]);
-        total += ms;
-        cudaEventDestroy(e0[i]); cudaEventDestroy(e1[i]);
+        CK(cudaStreamSynchronize(ctx->stream));
+        for (int i = 0; i < reps; ++i) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, e0[i], e1[i]);
+            total += ms;
+            cudaEventDestroy(e0[i]); cudaEventDestroy(e1[i]);
+        }
     }
     *ms_per_launch = (float)(total / reps);
     return rc;
@@ -845,8 +819,12 @@ int dcreg_icp_run_host_planes(dcreg_ctx* ctx, const dcreg_icp_params* params, co
         if (cb(user, T, hplanes, &npt) != 0) { ctx->err = "plane callback failed"; return DCREG_BAD_ARG; }
         CK(cudaMemcpyAsync(ctx->d_planes64, hplanes, (size_t)ctx->n_src * sizeof(double4), cudaMemcpyHostToDevice,
                            ctx->stream));
-        if ((rc = launch_reduce(ctx, ctx->d_src, ctx->d_planes64, true, ctx->n_src, nullptr,
-                                params->use_weight_derivative, ctx->d_state)))
+        k1::Pose P;                                   // the host holds the current pose in this mode
+        for (int r = 0; r < 3; ++r) {
+            for (int c = 0; c < 3; ++c) P.R[r * 3 + c] = T[r * 4 + c];
+            P.t[r] = T[r * 4 + 3];
+        }
+        if ((rc = launch_reduce(ctx, ctx->d_src, ctx->d_planes64, true, ctx->n_src, &P, params->use_weight_derivative)))
             return rc;
         if ((rc = nccl_allreduce_acc(ctx))) return rc;
         k2_step_kernel<<<1, 32, 0, ctx->stream>>>(ctx->d_acc, ctx->d_state, *params, dlog, log_cap);

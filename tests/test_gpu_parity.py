@@ -121,9 +121,16 @@ def test_pcg_seam(ctx):
 
 def test_k2_singular_and_nonfinite(ctx):
     from dcreg_b200 import default_params, api
-    v = np.zeros(27)                                   # H = 0: singular blocks, QR gives zero
+    # H = 0: singular blocks -> Schur conds = inf (icp_test_runner.cpp:2464-2469); the pivoted-QR solve of an
+    # all-zero matrix divides by a zero pivot exactly like Eigen's, the loop then aborts (:1942-1950)
+    v = np.zeros(27)
     a, dx, rc = ctx.analyze_and_solve(v, default_params())
-    assert rc == 0 and np.all(dx == 0) and math.isinf(a.cond_schur_rot) and math.isinf(a.cond_full)
+    assert rc == api.NONFINITE_UPDATE and math.isinf(a.cond_schur_rot) and math.isinf(a.cond_full)
+    assert a.is_degenerate == 0
+    # rank-deficient but non-zero H (pure translation information): finite basic solution, zero rotation part
+    H = np.zeros((6, 6)); H[3:, 3:] = np.diag([4.0, 2.0, 1.0]); g = np.array([0, 0, 0, 4.0, 2.0, 1.0])
+    a, dx, rc = ctx.analyze_and_solve(o.pack27(H, g), default_params(handling="NONE_HAND", detection="NONE_DETE"))
+    assert rc == 0 and np.allclose(dx, [0, 0, 0, 1, 1, 1])
     v[:] = np.nan
     a, dx, rc = ctx.analyze_and_solve(v, default_params(handling="NONE_HAND", detection="NONE_DETE"))
     assert rc == api.NONFINITE_UPDATE
