@@ -1,4 +1,4 @@
-// corr.cuh - device correspondence stage: hash-grid exact 5-NN within radius + 5x3 plane fit.
+// corr.cuh - device correspondence stage: uniform-grid exact 5-NN within radius + 5x3 plane fit.
 //
 // Replaces (reference file:line):
 //   ICPContext::setTargetCloud kd-tree build           DCReg/include/utils.hpp:393-424
@@ -10,6 +10,12 @@
 // around q's cell, so an exact 5-NN over those cells reproduces the accept set of the kd-tree
 // (SURVEY.md §7 step 6).  Distances are float32 sums of float32 squared differences, as in FLANN's
 // L2_Simple functor that PCL's KdTreeFLANN uses; ties are broken by original point index.
+//
+// Layout in HBM: target points grouped by cell (float4: x, y, z, bit-cast original index).
+//   dense mode : cells of the target's bounding box in x-fastest linear order + cell_start[ncells + 1];
+//                the 3 x-adjacent cells of a row are ONE contiguous point range, so a query scans 9 ranges.
+//   hash mode  : open-addressing table keyed by the packed cell coordinates (fallback when the bounding box
+//                has more than kMaxDenseCells cells); a query probes 27 cells.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -18,15 +24,22 @@
 namespace corr {
 
 constexpr unsigned long long kEmptyKey = ~0ull;
+constexpr long long kMaxDenseCells = 1ll << 27;
 
 struct Grid {
-    unsigned long long* keys;   // capacity entries, kEmptyKey = free
-    int* cell_start;            // capacity
-    int* cell_count;            // capacity
-    float4* pts;                // n target points grouped by cell: (x, y, z, bit-cast original index)
-    unsigned int mask;          // capacity - 1 (capacity is a power of two)
+    float4* pts;                // n target points grouped by cell
     int n;
+    int dense;                  // 1: dense mode, 0: hash mode
     double inv_cell;            // 1 / cell edge
+    // dense mode
+    int ox, oy, oz;             // cell coordinates of the bounding box's minimum corner
+    int nx, ny, nz;
+    int* cell_start;            // [nx*ny*nz + 1]
+    // hash mode
+    unsigned long long* keys;   // capacity entries, kEmptyKey = free
+    int* hstart;                // capacity
+    int* hcount;                // capacity
+    unsigned int mask;          // capacity - 1 (capacity is a power of two)
 };
 
 __host__ __device__ __forceinline__ int cell_coord(float v, double inv_cell) {
@@ -34,9 +47,8 @@ __host__ __device__ __forceinline__ int cell_coord(float v, double inv_cell) {
 }
 
 __host__ __device__ __forceinline__ unsigned long long pack_key(int ix, int iy, int iz) {
-    const unsigned long long B = 1ull << 20;
-    return ((unsigned long long)(ix + (long long)B) << 42) | ((unsigned long long)(iy + (long long)B) << 21) |
-           (unsigned long long)(iz + (long long)B);
+    const long long B = 1ll << 20;
+    return ((unsigned long long)(ix + B) << 42) | ((unsigned long long)(iy + B) << 21) | (unsigned long long)(iz + B);
 }
 
 __host__ __device__ __forceinline__ unsigned int hash_key(unsigned long long k) {
@@ -44,11 +56,43 @@ __host__ __device__ __forceinline__ unsigned int hash_key(unsigned long long k) 
     return (unsigned int)k;
 }
 
+__device__ __forceinline__ int dense_index(const Grid& g, int cx, int cy, int cz) {
+    return ((cz - g.oz) * g.ny + (cy - g.oy)) * g.nx + (cx - g.ox);
+}
+
 // ---- build -----------------------------------------------------------------------------------
-__global__ void grid_insert_kernel(const float4* __restrict__ tgt, int n, Grid g, int* __restrict__ pt_slot) {
+// bounds[0..2] = min cell coords, bounds[3..5] = max cell coords (initialised to +-2^30 by the host)
+__global__ void grid_bounds_kernel(const float4* __restrict__ pts, int n, double inv_cell, int* __restrict__ bounds) {
+    int lo[3] = {1 << 30, 1 << 30, 1 << 30}, hi[3] = {-(1 << 30), -(1 << 30), -(1 << 30)};
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float4 p = pts[i];
+        const int c[3] = {cell_coord(p.x, inv_cell), cell_coord(p.y, inv_cell), cell_coord(p.z, inv_cell)};
+        for (int k = 0; k < 3; ++k) { lo[k] = min(lo[k], c[k]); hi[k] = max(hi[k], c[k]); }
+    }
+    for (int k = 0; k < 3; ++k) {
+        for (int off = 16; off > 0; off >>= 1) {
+            lo[k] = min(lo[k], __shfl_xor_sync(0xffffffffu, lo[k], off));
+            hi[k] = max(hi[k], __shfl_xor_sync(0xffffffffu, hi[k], off));
+        }
+        if ((threadIdx.x & 31) == 0) { atomicMin(&bounds[k], lo[k]); atomicMax(&bounds[3 + k], hi[k]); }
+    }
+}
+
+// cell id of a point: dense linear index (clamped into the box when `clamp`), or hash slot (insert mode)
+__global__ void grid_count_dense_kernel(const float4* __restrict__ pts, int n, Grid g, int* __restrict__ pt_cell,
+                                        int* __restrict__ counts) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const float4 p = tgt[i];
+    const float4 p = pts[i];
+    const int c = dense_index(g, cell_coord(p.x, g.inv_cell), cell_coord(p.y, g.inv_cell), cell_coord(p.z, g.inv_cell));
+    pt_cell[i] = c;
+    atomicAdd(&counts[c], 1);
+}
+
+__global__ void grid_insert_hash_kernel(const float4* __restrict__ pts, int n, Grid g, int* __restrict__ pt_slot) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 p = pts[i];
     const unsigned long long key = pack_key(cell_coord(p.x, g.inv_cell), cell_coord(p.y, g.inv_cell),
                                             cell_coord(p.z, g.inv_cell));
     unsigned int slot = hash_key(key) & g.mask;
@@ -58,17 +102,17 @@ __global__ void grid_insert_kernel(const float4* __restrict__ tgt, int n, Grid g
         slot = (slot + 1) & g.mask;
     }
     pt_slot[i] = (int)slot;
-    atomicAdd(&g.cell_count[slot], 1);
+    atomicAdd(&g.hcount[slot], 1);
 }
 
-// exclusive scan of int array, three phases (tile sums, scan of tile sums, tile rescan)
+// exclusive scan of an int array, three phases (tile sums, scan of tile sums, tile rescan)
 constexpr int kScanTile = 2048;   // 256 threads x 8
 __global__ void scan_tile_sums_kernel(const int* __restrict__ in, int n, int* __restrict__ tile_sums) {
     __shared__ int sh[256];
-    const int base = blockIdx.x * kScanTile;
+    const long long base = (long long)blockIdx.x * kScanTile;
     int s = 0;
     for (int k = 0; k < 8; ++k) {
-        const int idx = base + threadIdx.x * 8 + k;
+        const long long idx = base + threadIdx.x * 8 + k;
         if (idx < n) s += in[idx];
     }
     sh[threadIdx.x] = s;
@@ -104,11 +148,11 @@ __global__ void scan_tile_offsets_kernel(int* tile_sums, int ntiles) {   // sing
 __global__ void scan_tile_apply_kernel(const int* __restrict__ in, int n, const int* __restrict__ tile_offsets,
                                        int* __restrict__ out) {
     __shared__ int sh[256];
-    const int base = blockIdx.x * kScanTile;
+    const long long base = (long long)blockIdx.x * kScanTile;
     int loc[8];
     int s = 0;
     for (int k = 0; k < 8; ++k) {
-        const int idx = base + threadIdx.x * 8 + k;
+        const long long idx = base + threadIdx.x * 8 + k;
         loc[k] = idx < n ? in[idx] : 0;
         s += loc[k];
     }
@@ -122,30 +166,34 @@ __global__ void scan_tile_apply_kernel(const int* __restrict__ in, int n, const 
     }
     int run = tile_offsets[blockIdx.x] + sh[threadIdx.x] - s;
     for (int k = 0; k < 8; ++k) {
-        const int idx = base + threadIdx.x * 8 + k;
+        const long long idx = base + threadIdx.x * 8 + k;
         if (idx < n) out[idx] = run;
         run += loc[k];
     }
 }
 
-__global__ void grid_scatter_kernel(const float4* __restrict__ tgt, int n, Grid g, const int* __restrict__ pt_slot,
-                                    int* __restrict__ fill) {
+// scatter points into their cell's range; `start` is the exclusive scan of the per-cell counts
+__global__ void grid_scatter_kernel(const float4* __restrict__ pts, int n, const int* __restrict__ pt_cell,
+                                    const int* __restrict__ start, int* __restrict__ fill, float4* __restrict__ out,
+                                    int keep_w) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const int slot = pt_slot[i];
-    const int pos = g.cell_start[slot] + atomicAdd(&fill[slot], 1);
-    float4 p = tgt[i];
-    p.w = __int_as_float(i);
-    g.pts[pos] = p;
+    const int c = pt_cell[i];
+    const int pos = start[c] + atomicAdd(&fill[c], 1);
+    float4 p = pts[i];
+    if (!keep_w) p.w = __int_as_float(i);
+    out[pos] = p;
 }
 
 // deterministic order inside every cell: sort by original index (insertion sort, cells are small)
-__global__ void grid_sort_cells_kernel(Grid g, unsigned int capacity) {
-    const unsigned int slot = blockIdx.x * blockDim.x + threadIdx.x;
-    if (slot >= capacity) return;
-    const int cnt = g.cell_count[slot];
+__global__ void grid_sort_cells_kernel(float4* pts, const int* __restrict__ start, const int* __restrict__ count,
+                                       const int* __restrict__ start_next, long long ncells) {
+    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncells) return;
+    const int s = start[c];
+    const int cnt = count ? count[c] : (start_next[c] - s);
     if (cnt < 2) return;
-    float4* p = g.pts + g.cell_start[slot];
+    float4* p = pts + s;
     for (int i = 1; i < cnt; ++i) {
         const float4 v = p[i];
         const int key = __float_as_int(v.w);
@@ -153,6 +201,24 @@ __global__ void grid_sort_cells_kernel(Grid g, unsigned int capacity) {
         while (j >= 0 && __float_as_int(p[j].w) > key) { p[j + 1] = p[j]; --j; }
         p[j + 1] = v;
     }
+}
+
+// cell of a (transformed) source point for the spatial sort of the source cloud, clamped into the target box
+__global__ void source_cell_kernel(const float4* __restrict__ src, int n, Grid g, const double* __restrict__ T,
+                                   int* __restrict__ pt_cell, int* __restrict__ counts) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 p = src[i];
+    const double px = p.x, py = p.y, pz = p.z;
+    const float qx = (float)(T[0] * px + T[1] * py + T[2] * pz + T[3]);
+    const float qy = (float)(T[4] * px + T[5] * py + T[6] * pz + T[7]);
+    const float qz = (float)(T[8] * px + T[9] * py + T[10] * pz + T[11]);
+    const int cx = min(max(cell_coord(qx, g.inv_cell) - g.ox, 0), g.nx - 1);
+    const int cy = min(max(cell_coord(qy, g.inv_cell) - g.oy, 0), g.ny - 1);
+    const int cz = min(max(cell_coord(qz, g.inv_cell) - g.oz, 0), g.nz - 1);
+    const int c = (cz * g.ny + cy) * g.nx + cx;
+    pt_cell[i] = c;
+    atomicAdd(&counts[c], 1);
 }
 
 // ---- query -----------------------------------------------------------------------------------
@@ -168,7 +234,6 @@ __device__ __forceinline__ void knn_init(Knn5& k) {
 }
 
 __device__ __forceinline__ void knn_insert(Knn5& k, float d2, int pos, int idx) {
-    if (d2 > k.d2[4] || (d2 == k.d2[4] && idx > k.idx[4])) return;
     k.d2[4] = d2; k.pos[4] = pos; k.idx[4] = idx;
 #pragma unroll
     for (int i = 4; i > 0; --i) {
@@ -181,30 +246,63 @@ __device__ __forceinline__ void knn_insert(Knn5& k, float d2, int pos, int idx) 
     }
 }
 
+// FLANN L2_Simple: float differences, float accumulation, x then y then z (no FMA contraction)
+__device__ __forceinline__ float dist2(float qx, float qy, float qz, const float4& p) {
+    const float ex = __fsub_rn(qx, p.x), ey = __fsub_rn(qy, p.y), ez = __fsub_rn(qz, p.z);
+    return __fadd_rn(__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)), __fmul_rn(ez, ez));
+}
+
+__device__ __forceinline__ void knn_scan_range(const float4* __restrict__ pts, int s, int e, float qx, float qy,
+                                               float qz, Knn5& k) {
+    int j = s;
+    for (; j + 1 < e; j += 2) {                       // two candidates per trip: both loads in flight
+        const float4 p0 = __ldg(&pts[j]), p1 = __ldg(&pts[j + 1]);
+        const float a0 = dist2(qx, qy, qz, p0), a1 = dist2(qx, qy, qz, p1);
+        const int i0 = __float_as_int(p0.w), i1 = __float_as_int(p1.w);
+        if (a0 < k.d2[4] || (a0 == k.d2[4] && i0 < k.idx[4])) knn_insert(k, a0, j, i0);
+        if (a1 < k.d2[4] || (a1 == k.d2[4] && i1 < k.idx[4])) knn_insert(k, a1, j + 1, i1);
+    }
+    if (j < e) {
+        const float4 p0 = __ldg(&pts[j]);
+        const float a0 = dist2(qx, qy, qz, p0);
+        const int i0 = __float_as_int(p0.w);
+        if (a0 < k.d2[4] || (a0 == k.d2[4] && i0 < k.idx[4])) knn_insert(k, a0, j, i0);
+    }
+}
+
 __device__ __forceinline__ void knn_search(const Grid& g, float qx, float qy, float qz, Knn5& k) {
     const int cx = cell_coord(qx, g.inv_cell), cy = cell_coord(qy, g.inv_cell), cz = cell_coord(qz, g.inv_cell);
-    for (int dz = -1; dz <= 1; ++dz)
-        for (int dy = -1; dy <= 1; ++dy)
-            for (int dx = -1; dx <= 1; ++dx) {
-                const unsigned long long key = pack_key(cx + dx, cy + dy, cz + dz);
-                unsigned int slot = hash_key(key) & g.mask;
-                int start = 0, cnt = 0;
-                while (true) {
-                    const unsigned long long kk = __ldg(&g.keys[slot]);
-                    if (kk == key) { start = __ldg(&g.cell_start[slot]); cnt = __ldg(&g.cell_count[slot]); break; }
-                    if (kk == kEmptyKey) break;
-                    slot = (slot + 1) & g.mask;
+    if (g.dense) {
+        const int x0 = max(cx - 1 - g.ox, 0), x1 = min(cx + 1 - g.ox, g.nx - 1);
+        if (x0 > x1) return;
+        // gather the 9 row ranges first (independent loads), then scan them
+        int rs[9], re[9];
+#pragma unroll
+        for (int r = 0; r < 9; ++r) {
+            const int yy = cy - g.oy + (r % 3) - 1, zz = cz - g.oz + (r / 3) - 1;
+            const bool ok = (yy >= 0) && (yy < g.ny) && (zz >= 0) && (zz < g.nz);
+            const int row = (zz * g.ny + yy) * g.nx;
+            rs[r] = ok ? __ldg(&g.cell_start[row + x0]) : 0;
+            re[r] = ok ? __ldg(&g.cell_start[row + x1 + 1]) : 0;
+        }
+#pragma unroll
+        for (int r = 0; r < 9; ++r) knn_scan_range(g.pts, rs[r], re[r], qx, qy, qz, k);
+    } else {
+        for (int dz = -1; dz <= 1; ++dz)
+            for (int dy = -1; dy <= 1; ++dy)
+                for (int dx = -1; dx <= 1; ++dx) {
+                    const unsigned long long key = pack_key(cx + dx, cy + dy, cz + dz);
+                    unsigned int slot = hash_key(key) & g.mask;
+                    int start = 0, cnt = 0;
+                    while (true) {
+                        const unsigned long long kk = __ldg(&g.keys[slot]);
+                        if (kk == key) { start = __ldg(&g.hstart[slot]); cnt = __ldg(&g.hcount[slot]); break; }
+                        if (kk == kEmptyKey) break;
+                        slot = (slot + 1) & g.mask;
+                    }
+                    knn_scan_range(g.pts, start, start + cnt, qx, qy, qz, k);
                 }
-                for (int j = 0; j < cnt; ++j) {
-                    const float4 p = __ldg(&g.pts[start + j]);
-                    // FLANN L2_Simple: float diff, float accumulate, x then y then z (no FMA contraction)
-                    const float ex = __fsub_rn(qx, p.x), ey = __fsub_rn(qy, p.y), ez = __fsub_rn(qz, p.z);
-                    float d2 = __fmul_rn(ex, ex);
-                    d2 = __fadd_rn(d2, __fmul_rn(ey, ey));
-                    d2 = __fadd_rn(d2, __fmul_rn(ez, ez));
-                    knn_insert(k, d2, start + j, __float_as_int(p.w));
-                }
-            }
+    }
 }
 
 // Plane through the 5 neighbours: least squares of [nb] x = -1, n = x/|x|, d = 1/|x|, gates

@@ -24,7 +24,7 @@
 #include "../../include/dcreg_b200.h"
 #include "corr.cuh"
 #include "k1_reduce.cuh"
-#include "k1_mma.cuh"
+#include "k1_stream.cuh"
 #include "k2_solve.cuh"
 
 using k2::IcpState;
@@ -60,52 +60,62 @@ __device__ __forceinline__ bool last_block_ticket(unsigned int* counter) {
 }
 
 struct IterArgs {
-    const float4* src;
+    const float4* src;        // source points, w = bit-cast original index (spatially sorted copy or the original)
     long long n;
     corr::Grid grid;
     IcpState* state;
     double* partials;
     unsigned int* counter;
     double* acc;
-    double4* planes_out;      // optional: materialise the planes (seam 1 / debugging)
+    double4* planes_out;      // optional: materialise the planes at the ORIGINAL slot index (seam 1)
     dcreg_icp_params prm;
 };
 
-// One ICP iteration: stage S1 (correspondences, plane fit, residual, weight) fused with S4-S5
-// (Jacobian, normal equations) and, on one GPU, S6-S9 (analysis, solve, update, convergence).
-__global__ void __launch_bounds__(kBlock) icp_iteration_kernel(IterArgs a) {
-    __shared__ double smem[(kBlock / 32) * kAcc];
+struct IterSmem {
+    double tbuf[kBlock / 32][8 * k1::kTRow];   // per-warp DMMA transpose buffers
+    k1::GramSmem gram;
+};
+
+// One ICP iteration on the device: stage S1 (correspondences: exact 5-NN in the grid, plane fit, gates) fused with
+// the residual / weight / Jacobian row and the Gram accumulation (S4-S5).  One source point per thread per trip;
+// no per-thread accumulator block: the 8x8 Gram is accumulated with DMMA (two registers per lane).
+template <bool kUseWd>
+__global__ void __launch_bounds__(kBlock, 2) icp_iteration_kernel(const __grid_constant__ IterArgs a) {
+    __shared__ IterSmem sm;
     if (a.state->done) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const k1::Pose P = load_pose(a.state);
-    k1::Acc acc;
-    k1::acc_zero(acc);
+    double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;
+    int neff = 0, npt = 0;
     const double r2max = a.prm.search_radius * a.prm.search_radius;
-    const bool use_wd = a.prm.use_weight_derivative != 0;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n;
+    const long long n32 = (a.n + 31) & ~31ll;                 // whole warps enter the DMMA section together
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n32;
          i += (long long)gridDim.x * blockDim.x) {
-        const float4 p4 = __ldg(&a.src[i]);
-        const double px = (double)p4.x, py = (double)p4.y, pz = (double)p4.z;
-        const float qx = (float)(P.R[0] * px + P.R[1] * py + P.R[2] * pz + P.t[0]);
-        const float qy = (float)(P.R[3] * px + P.R[4] * py + P.R[5] * pz + P.t[1]);
-        const float qz = (float)(P.R[6] * px + P.R[7] * py + P.R[8] * pz + P.t[2]);
-        corr::Knn5 nn;
-        corr::knn_init(nn);
-        corr::knn_search(a.grid, qx, qy, qz, nn);
-        double nx = 0.0, ny = 0.0, nz = 0.0, d = 0.0;
+        double px = 0.0, py = 0.0, pz = 0.0, nx = 0.0, ny = 0.0, nz = 0.0, d = 0.0;
         bool ok = false;
-        if (nn.pos[4] >= 0 && (double)nn.d2[4] < r2max) {            // icp_test_runner.cpp:1726
-            acc.npt += 1;                                              // :1731
-            ok = corr::fit_plane(a.grid, nn, a.prm.min_normal_norm, a.prm.plane_thickness, nx, ny, nz, d);
+        if (i < a.n) {
+            const float4 p4 = __ldg(&a.src[i]);
+            px = (double)p4.x; py = (double)p4.y; pz = (double)p4.z;
+            // q = fl32(R p + t)  (utils.hpp:630-636)
+            const float qx = (float)(P.R[0] * px + P.R[1] * py + P.R[2] * pz + P.t[0]);
+            const float qy = (float)(P.R[3] * px + P.R[4] * py + P.R[5] * pz + P.t[1]);
+            const float qz = (float)(P.R[6] * px + P.R[7] * py + P.R[8] * pz + P.t[2]);
+            corr::Knn5 nn;
+            corr::knn_init(nn);
+            corr::knn_search(a.grid, qx, qy, qz, nn);
+            if (nn.pos[4] >= 0 && (double)nn.d2[4] < r2max) {                // icp_test_runner.cpp:1726
+                npt += 1;                                                     // :1731
+                ok = corr::fit_plane(a.grid, nn, a.prm.min_normal_norm, a.prm.plane_thickness, nx, ny, nz, d);
+            }
+            if (a.planes_out)
+                a.planes_out[__float_as_int(p4.w)] = ok ? make_double4(nx, ny, nz, d) : make_double4(0.0, 0.0, 0.0, 0.0);
         }
-        if (a.planes_out) a.planes_out[i] = ok ? make_double4(nx, ny, nz, d) : make_double4(0.0, 0.0, 0.0, 0.0);
-        k1::accumulate_slot(acc, P, px, py, pz, nx, ny, nz, d, use_wd, ok);
+        double c[8];
+        k1::slot_front<kUseWd>(P, px, py, pz, nx, ny, nz, d, ok, c, neff);
+        __syncwarp();
+        k1::gram_accumulate_dmma(sm.tbuf[warp], lane, c, c0, c1, e0, e1);
     }
-    k1::block_reduce_store(acc, smem, a.partials + (size_t)blockIdx.x * kAcc);
-    if (last_block_ticket(a.counter)) {
-        __syncthreads();
-        k1::final_reduce(a.partials, gridDim.x, P.R, smem, a.acc);
-        if (threadIdx.x == 0) *a.counter = 0u;
-    }
+    k1::finish_block(c0 + e0, c1 + e1, neff, npt, sm.gram, a.partials, a.counter, a.state->R, a.acc);
 }
 
 // K2 as its own kernel (seam 3, and the sharded loop after the all-reduce).
@@ -117,7 +127,19 @@ __global__ void k2_step_kernel(const double* acc, IcpState* st, dcreg_icp_params
 
 __global__ void k2_analyze_kernel(const double* v27, dcreg_icp_params prm, dcreg_analysis* out, double* dx) {
     if (threadIdx.x != 0) return;
-    k2::analyze_and_solve(v27, prm, out, dx);
+    k2::analyze_and_solve<true>(v27, prm, out, dx);
+}
+
+// Post-run log fill: one thread per iteration record recomputes the FULL analysis from the record's H27
+// (same code, same inputs => identical mask / P / PCG counts as the in-loop critical path wrote) and thereby adds the
+// log-only quantities without putting them on the loop's critical path.
+__global__ void log_fill_kernel(dcreg_iter_log* log, int log_cap, const IcpState* st, dcreg_icp_params prm) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = st->iter < log_cap ? st->iter : log_cap;
+    if (i >= n) return;
+    if (log[i].status != DCREG_OK) return;
+    double dx[6];
+    k2::analyze_and_solve<true>(log[i].H27, prm, &log[i].analysis, dx);
 }
 
 __global__ void pcg_kernel(const double* A, const double* b, const double* P, int max_it, double tol, double* x,
@@ -160,7 +182,7 @@ __global__ void covariance_kernel(const IcpState* st, double* cov) {
 __global__ void pack_source_kernel(const float* __restrict__ in, long long n, int stride, float4* __restrict__ out) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    out[i] = make_float4(in[i * stride], in[i * stride + 1], in[i * stride + 2], 0.0f);
+    out[i] = make_float4(in[i * stride], in[i * stride + 1], in[i * stride + 2], __int_as_float((int)i));   // w = slot index
 }
 
 __global__ void planes_to_f32_kernel(const double4* __restrict__ in, long long n, float4* __restrict__ out) {
@@ -238,7 +260,11 @@ struct dcreg_ctx {
     float* d_stage = nullptr; size_t stage_bytes = 0;
 
     float4* d_tgt = nullptr; long long n_tgt = 0;
-    corr::Grid grid{}; unsigned int grid_capacity = 0; bool has_grid = false;
+    corr::Grid grid{}; long long grid_cells = 0; bool has_grid = false;
+    float4* d_src_sorted = nullptr; long long src_sorted_cap = 0;     // source in target-cell order (w = original index)
+    int* d_cell_tmp = nullptr; long long cell_tmp_cap = 0;            // counts / fill cursors for the source sort
+    int* d_pt_cell = nullptr; long long pt_cell_cap = 0;
+    int* d_tile_sums = nullptr; long long tile_sums_cap = 0;
     double cell_size = 0.0;
 
     double4* d_planes64 = nullptr; float4* d_planes32 = nullptr; long long planes_cap = 0;
@@ -281,7 +307,7 @@ int ensure_partials(dcreg_ctx* ctx, int blocks) {
     if (ctx->partials_blocks >= blocks) return DCREG_OK;
     if (ctx->d_partials) cudaFree(ctx->d_partials);
     ctx->d_partials = nullptr;
-    CK(cudaMalloc(&ctx->d_partials, (size_t)blocks * 72 * sizeof(double)));   // >= k1m::kPart and kAcc
+    CK(cudaMalloc(&ctx->d_partials, (size_t)blocks * 72 * sizeof(double)));   // >= k1s::kPart and kAcc
     ctx->partials_blocks = blocks;
     return DCREG_OK;
 }
@@ -329,58 +355,41 @@ int upload_points(dcreg_ctx* ctx, const float* xyz, long long n, int stride, flo
     return DCREG_OK;
 }
 
-template <typename PlaneT, bool kUseWd, int kMinBlocks, bool kDmma>
-int launch_reduce_t(dcreg_ctx* ctx, k1m::Args& a) {
-    auto kern = k1m::reduce_mma_kernel<PlaneT, kUseWd, kMinBlocks, kDmma>;
-    const size_t smem = sizeof(k1m::Smem<PlaneT>);
+template <typename PlaneT, bool kUseWd>
+int launch_reduce_t(dcreg_ctx* ctx, k1s::Args& a) {
+    auto kern = k1s::reduce_stream_kernel<PlaneT, kUseWd>;
+    const size_t smem = sizeof(k1s::Smem<PlaneT>);
     static int blocks_per_sm = 0;
     if (blocks_per_sm == 0) {
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         int nb = 0;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, k1m::kThreads, smem));
-        if (getenv("DCREG_K1_VERBOSE")) fprintf(stderr, "[dcreg] K1 smem %zu B/block, %d blocks/SM\n", smem, nb);
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, k1s::kThreads, smem));
         blocks_per_sm = nb > 0 ? nb : 1;
     }
     // persistent grid: every SM holds `blocks_per_sm` CTAs; warps take 32-slot chunks round-robin
     const long long nchunks = (a.n + 31) / 32;
     long long g = (long long)ctx->sm_count * blocks_per_sm;
-    const long long need = (nchunks + k1m::kWarpsPerBlock - 1) / k1m::kWarpsPerBlock;
+    const long long need = (nchunks + k1s::kWarpsPerBlock - 1) / k1s::kWarpsPerBlock;
     if (g > need) g = need;
     if (g < 1) g = 1;
     int rc = ensure_partials(ctx, (int)g);
     if (rc) return rc;
     a.partials = ctx->d_partials;
-    kern<<<(int)g, k1m::kThreads, smem, ctx->stream>>>(a);
+    kern<<<(int)g, k1s::kThreads, smem, ctx->stream>>>(a);
     ctx->launches++;
     CK(cudaGetLastError());
     return DCREG_OK;
 }
 
-template <int kMinBlocks, bool kDmma>
-int launch_reduce_v(dcreg_ctx* ctx, k1m::Args& a, bool f64, bool wd) {
-    if (wd) return f64 ? launch_reduce_t<double4, true, kMinBlocks, kDmma>(ctx, a) : launch_reduce_t<float4, true, kMinBlocks, kDmma>(ctx, a);
-    return f64 ? launch_reduce_t<double4, false, kMinBlocks, kDmma>(ctx, a) : launch_reduce_t<float4, false, kMinBlocks, kDmma>(ctx, a);
-}
-
-int k1_variant() {
-    static int v = -1;
-    if (v < 0) { const char* e = getenv("DCREG_K1_VARIANT"); v = e ? atoi(e) : 0; }
-    return v;
-}
-
 int launch_reduce(dcreg_ctx* ctx, const float4* d_src, const void* d_plane, bool f64, long long n,
                   const k1::Pose* pose, int use_wd) {
-    k1m::Args a{};
+    k1s::Args a{};
     a.src = d_src; a.plane = d_plane; a.n = n;
     if (pose) a.pose = *pose;
     a.counter = ctx->d_counter; a.acc = ctx->d_acc;
-    switch (k1_variant()) {
-        case 1: return launch_reduce_v<1, false>(ctx, a, f64, use_wd != 0);
-        case 2: return launch_reduce_v<2, false>(ctx, a, f64, use_wd != 0);
-        case 4: return launch_reduce_v<4, true>(ctx, a, f64, use_wd != 0);
-        default: return launch_reduce_v<3, true>(ctx, a, f64, use_wd != 0);
-    }
+    if (use_wd) return f64 ? launch_reduce_t<double4, true>(ctx, a) : launch_reduce_t<float4, true>(ctx, a);
+    return f64 ? launch_reduce_t<double4, false>(ctx, a) : launch_reduce_t<float4, false>(ctx, a);
 }
 
 int nccl_allreduce_acc(dcreg_ctx* ctx) {
@@ -476,7 +485,8 @@ int dcreg_destroy(dcreg_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    void* ptrs[] = {ctx->d_src, ctx->d_stage, ctx->d_tgt, ctx->grid.keys, ctx->grid.cell_start, ctx->grid.cell_count,
+    void* ptrs[] = {ctx->d_src, ctx->d_stage, ctx->d_tgt, ctx->grid.keys, ctx->grid.cell_start, ctx->grid.hstart,
+                    ctx->grid.hcount, ctx->d_src_sorted, ctx->d_cell_tmp, ctx->d_pt_cell, ctx->d_tile_sums,
                     ctx->grid.pts, ctx->d_planes64, ctx->d_planes32, ctx->d_partials, ctx->d_counter, ctx->d_acc,
                     ctx->d_state, ctx->d_log, ctx->d_small, ctx->d_analysis, ctx->d_flush};
     for (void* p : ptrs)
@@ -515,6 +525,23 @@ int dcreg_set_global_source_count(dcreg_ctx* ctx, int64_t n_total) {
     return DCREG_OK;
 }
 
+// exclusive scan of `n` ints (in -> out) on ctx's stream; tile_sums is ctx-owned scratch
+static int device_exclusive_scan(dcreg_ctx* ctx, const int* in, long long n, int* out) {
+    const int ntiles = (int)((n + corr::kScanTile - 1) / corr::kScanTile);
+    if (ctx->tile_sums_cap < ntiles) {
+        if (ctx->d_tile_sums) cudaFree(ctx->d_tile_sums);
+        ctx->d_tile_sums = nullptr; ctx->tile_sums_cap = 0;
+        CK(cudaMalloc(&ctx->d_tile_sums, (size_t)ntiles * sizeof(int)));
+        ctx->tile_sums_cap = ntiles;
+    }
+    corr::scan_tile_sums_kernel<<<ntiles, 256, 0, ctx->stream>>>(in, (int)n, ctx->d_tile_sums);
+    corr::scan_tile_offsets_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->d_tile_sums, ntiles);
+    corr::scan_tile_apply_kernel<<<ntiles, 256, 0, ctx->stream>>>(in, (int)n, ctx->d_tile_sums, out);
+    ctx->launches += 3;
+    CK(cudaGetLastError());
+    return DCREG_OK;
+}
+
 int dcreg_set_target(dcreg_ctx* ctx, const float* xyz, int64_t m, int stride, double cell_size) {
     if (!ctx) return DCREG_BAD_ARG;
     if (!xyz || m <= 0 || stride < 3 || !(cell_size > 0.0) || m > 0x7fffffffLL) {
@@ -522,7 +549,7 @@ int dcreg_set_target(dcreg_ctx* ctx, const float* xyz, int64_t m, int stride, do
         return DCREG_BAD_ARG;
     }
     CK(cudaSetDevice(ctx->device));
-    void* old[] = {ctx->d_tgt, ctx->grid.keys, ctx->grid.cell_start, ctx->grid.cell_count, ctx->grid.pts};
+    void* old[] = {ctx->d_tgt, ctx->grid.keys, ctx->grid.cell_start, ctx->grid.hstart, ctx->grid.hcount, ctx->grid.pts};
     for (void* p : old)
         if (p) cudaFree(p);
     ctx->d_tgt = nullptr; ctx->grid = corr::Grid{}; ctx->has_grid = false;
@@ -530,49 +557,122 @@ int dcreg_set_target(dcreg_ctx* ctx, const float* xyz, int64_t m, int stride, do
     ctx->n_tgt = m;
     int rc = upload_points(ctx, xyz, m, stride, ctx->d_tgt);
     if (rc) return rc;
-    unsigned int cap = 1024;
-    while ((long long)cap < 2 * m) cap <<= 1;
-    ctx->grid_capacity = cap;
     corr::Grid& g = ctx->grid;
-    g.mask = cap - 1; g.n = (int)m; g.inv_cell = 1.0 / cell_size;
+    g.n = (int)m; g.inv_cell = 1.0 / cell_size;
     ctx->cell_size = cell_size;
-    CK(cudaMalloc(&g.keys, (size_t)cap * sizeof(unsigned long long)));
-    CK(cudaMalloc(&g.cell_start, (size_t)cap * sizeof(int)));
-    CK(cudaMalloc(&g.cell_count, (size_t)cap * sizeof(int)));
     CK(cudaMalloc(&g.pts, (size_t)m * sizeof(float4)));
-    int *pt_slot = nullptr, *fill = nullptr, *tile_sums = nullptr;
-    const int ntiles = (int)((cap + corr::kScanTile - 1) / corr::kScanTile);
-    CK(cudaMalloc(&pt_slot, (size_t)m * sizeof(int)));
-    CK(cudaMalloc(&fill, (size_t)cap * sizeof(int)));
-    CK(cudaMalloc(&tile_sums, (size_t)ntiles * sizeof(int)));
-    CK(cudaMemsetAsync(g.keys, 0xff, (size_t)cap * sizeof(unsigned long long), ctx->stream));
-    CK(cudaMemsetAsync(g.cell_count, 0, (size_t)cap * sizeof(int), ctx->stream));
-    CK(cudaMemsetAsync(fill, 0, (size_t)cap * sizeof(int), ctx->stream));
+    // bounding box in cell coordinates
+    int hb[6] = {1 << 30, 1 << 30, 1 << 30, -(1 << 30), -(1 << 30), -(1 << 30)};
+    int* d_bounds = (int*)(ctx->d_small + 512);
+    CK(cudaMemcpyAsync(d_bounds, hb, sizeof(hb), cudaMemcpyHostToDevice, ctx->stream));
+    corr::grid_bounds_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(ctx->d_tgt, (int)m, g.inv_cell, d_bounds);
+    ctx->launches++;
+    CK(cudaMemcpyAsync(hb, d_bounds, sizeof(hb), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (hb[0] < -(1 << 19) || hb[3] > (1 << 19) || hb[1] < -(1 << 19) || hb[4] > (1 << 19) || hb[2] < -(1 << 19) ||
+        hb[5] > (1 << 19)) {
+        ctx->err = "dcreg_set_target: coordinates / cell_size exceed the +-2^19 cell range (NaN or huge coordinates?)";
+        return DCREG_BAD_ARG;
+    }
+    const long long nx = (long long)hb[3] - hb[0] + 1, ny = (long long)hb[4] - hb[1] + 1, nz = (long long)hb[5] - hb[2] + 1;
+    const long long ncells = nx * ny * nz;
     const unsigned nb = (unsigned)((m + 255) / 256);
-    corr::grid_insert_kernel<<<nb, 256, 0, ctx->stream>>>(ctx->d_tgt, (int)m, g, pt_slot);
-    corr::scan_tile_sums_kernel<<<ntiles, 256, 0, ctx->stream>>>(g.cell_count, (int)cap, tile_sums);
-    corr::scan_tile_offsets_kernel<<<1, 1024, 0, ctx->stream>>>(tile_sums, ntiles);
-    corr::scan_tile_apply_kernel<<<ntiles, 256, 0, ctx->stream>>>(g.cell_count, (int)cap, tile_sums, g.cell_start);
-    corr::grid_scatter_kernel<<<nb, 256, 0, ctx->stream>>>(ctx->d_tgt, (int)m, g, pt_slot, fill);
-    corr::grid_sort_cells_kernel<<<(cap + 255) / 256, 256, 0, ctx->stream>>>(g, cap);
-    ctx->launches += 6;
-    cudaError_t e = cudaStreamSynchronize(ctx->stream);
-    cudaFree(pt_slot); cudaFree(fill); cudaFree(tile_sums);
+    int *pt_cell = nullptr, *fill = nullptr, *counts = nullptr;
+    CK(cudaMalloc(&pt_cell, (size_t)m * sizeof(int)));
+    cudaError_t e = cudaSuccess;
+    if (ncells <= corr::kMaxDenseCells) {
+        g.dense = 1; g.ox = hb[0]; g.oy = hb[1]; g.oz = hb[2]; g.nx = (int)nx; g.ny = (int)ny; g.nz = (int)nz;
+        ctx->grid_cells = ncells;
+        CK(cudaMalloc(&g.cell_start, (size_t)(ncells + 1) * sizeof(int)));
+        CK(cudaMalloc(&counts, (size_t)(ncells + 1) * sizeof(int)));
+        CK(cudaMalloc(&fill, (size_t)ncells * sizeof(int)));
+        CK(cudaMemsetAsync(counts, 0, (size_t)(ncells + 1) * sizeof(int), ctx->stream));
+        CK(cudaMemsetAsync(fill, 0, (size_t)ncells * sizeof(int), ctx->stream));
+        corr::grid_count_dense_kernel<<<nb, 256, 0, ctx->stream>>>(ctx->d_tgt, (int)m, g, pt_cell, counts);
+        if ((rc = device_exclusive_scan(ctx, counts, ncells + 1, g.cell_start))) return rc;
+        corr::grid_scatter_kernel<<<nb, 256, 0, ctx->stream>>>(ctx->d_tgt, (int)m, pt_cell, g.cell_start, fill, g.pts, 0);
+        corr::grid_sort_cells_kernel<<<(unsigned)((ncells + 255) / 256), 256, 0, ctx->stream>>>(g.pts, g.cell_start, nullptr,
+                                                                                               g.cell_start + 1, ncells);
+        ctx->launches += 3;
+        e = cudaStreamSynchronize(ctx->stream);
+    } else {
+        unsigned int cap = 1024;
+        while ((long long)cap < 2 * m) cap <<= 1;
+        g.dense = 0; g.mask = cap - 1;
+        ctx->grid_cells = 0;
+        CK(cudaMalloc(&g.keys, (size_t)cap * sizeof(unsigned long long)));
+        CK(cudaMalloc(&g.hstart, (size_t)cap * sizeof(int)));
+        CK(cudaMalloc(&g.hcount, (size_t)cap * sizeof(int)));
+        CK(cudaMalloc(&fill, (size_t)cap * sizeof(int)));
+        CK(cudaMemsetAsync(g.keys, 0xff, (size_t)cap * sizeof(unsigned long long), ctx->stream));
+        CK(cudaMemsetAsync(g.hcount, 0, (size_t)cap * sizeof(int), ctx->stream));
+        CK(cudaMemsetAsync(fill, 0, (size_t)cap * sizeof(int), ctx->stream));
+        corr::grid_insert_hash_kernel<<<nb, 256, 0, ctx->stream>>>(ctx->d_tgt, (int)m, g, pt_cell);
+        if ((rc = device_exclusive_scan(ctx, g.hcount, cap, g.hstart))) return rc;
+        corr::grid_scatter_kernel<<<nb, 256, 0, ctx->stream>>>(ctx->d_tgt, (int)m, pt_cell, g.hstart, fill, g.pts, 0);
+        corr::grid_sort_cells_kernel<<<(cap + 255) / 256, 256, 0, ctx->stream>>>(g.pts, g.hstart, g.hcount, nullptr, cap);
+        ctx->launches += 3;
+        e = cudaStreamSynchronize(ctx->stream);
+    }
+    cudaFree(pt_cell); cudaFree(fill);
+    if (counts) cudaFree(counts);
     if (e != cudaSuccess) { ctx->err = std::string("grid build: ") + cudaGetErrorString(e); return DCREG_CUDA_ERROR; }
     CK(cudaGetLastError());
     ctx->has_grid = true;
     return DCREG_OK;
 }
 
-static int launch_iteration(dcreg_ctx* ctx, const dcreg_icp_params* prm, double4* planes_out) {
+// Spatial sort of the source by the target cell of T*p (dense grids only): consecutive threads of the iteration
+// kernel then query neighbouring cells, so their candidate loads hit the same lines and their trip counts agree.
+// The sorted copy carries the original index in .w; the pose moves little during ICP, so one sort per run suffices.
+static int sort_source_by_cell(dcreg_ctx* ctx, const double T[16], const float4** src_out) {
+    *src_out = ctx->d_src;
+    if (!ctx->grid.dense || ctx->n_src > 0x7fffffffLL) return DCREG_OK;
+    const long long n = ctx->n_src, ncells = ctx->grid_cells;
+    if (ctx->src_sorted_cap < n) {
+        if (ctx->d_src_sorted) cudaFree(ctx->d_src_sorted);
+        if (ctx->d_pt_cell) cudaFree(ctx->d_pt_cell);
+        ctx->d_src_sorted = nullptr; ctx->d_pt_cell = nullptr; ctx->src_sorted_cap = 0;
+        CK(cudaMalloc(&ctx->d_src_sorted, (size_t)n * sizeof(float4)));
+        CK(cudaMalloc(&ctx->d_pt_cell, (size_t)n * sizeof(int)));
+        ctx->src_sorted_cap = n;
+    }
+    if (ctx->cell_tmp_cap < 3 * (ncells + 1)) {
+        if (ctx->d_cell_tmp) cudaFree(ctx->d_cell_tmp);
+        ctx->d_cell_tmp = nullptr; ctx->cell_tmp_cap = 0;
+        CK(cudaMalloc(&ctx->d_cell_tmp, (size_t)3 * (ncells + 1) * sizeof(int)));
+        ctx->cell_tmp_cap = 3 * (ncells + 1);
+    }
+    int* counts = ctx->d_cell_tmp;
+    int* start = counts + (ncells + 1);
+    int* fill = start + (ncells + 1);
+    CK(cudaMemsetAsync(counts, 0, (size_t)(ncells + 1) * sizeof(int), ctx->stream));
+    CK(cudaMemsetAsync(fill, 0, (size_t)ncells * sizeof(int), ctx->stream));
+    double* dT = ctx->d_small + 640;
+    CK(cudaMemcpyAsync(dT, T, 12 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    const unsigned nb = (unsigned)((n + 255) / 256);
+    corr::source_cell_kernel<<<nb, 256, 0, ctx->stream>>>(ctx->d_src, (int)n, ctx->grid, dT, ctx->d_pt_cell, counts);
+    int rc = device_exclusive_scan(ctx, counts, ncells + 1, start);
+    if (rc) return rc;
+    corr::grid_scatter_kernel<<<nb, 256, 0, ctx->stream>>>(ctx->d_src, (int)n, ctx->d_pt_cell, start, fill, ctx->d_src_sorted, 0);
+    corr::grid_sort_cells_kernel<<<(unsigned)((ncells + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_src_sorted, start, nullptr,
+                                                                                           start + 1, ncells);
+    ctx->launches += 3;
+    CK(cudaGetLastError());
+    *src_out = ctx->d_src_sorted;
+    return DCREG_OK;
+}
+
+static int launch_iteration(dcreg_ctx* ctx, const dcreg_icp_params* prm, const float4* src, double4* planes_out) {
     const int grid = stream_grid(ctx, ctx->n_src, 16);
     int rc = ensure_partials(ctx, grid);
     if (rc) return rc;
     IterArgs a{};
-    a.src = ctx->d_src; a.n = ctx->n_src; a.grid = ctx->grid; a.state = ctx->d_state;
+    a.src = src; a.n = ctx->n_src; a.grid = ctx->grid; a.state = ctx->d_state;
     a.partials = ctx->d_partials; a.counter = ctx->d_counter; a.acc = ctx->d_acc;
     a.planes_out = planes_out; a.prm = *prm;
-    icp_iteration_kernel<<<grid, kBlock, 0, ctx->stream>>>(a);
+    if (prm->use_weight_derivative) icp_iteration_kernel<true><<<grid, kBlock, 0, ctx->stream>>>(a);
+    else icp_iteration_kernel<false><<<grid, kBlock, 0, ctx->stream>>>(a);
     ctx->launches++;
     CK(cudaGetLastError());
     return DCREG_OK;
@@ -598,7 +698,7 @@ int dcreg_find_planes(dcreg_ctx* ctx, const double T[16], double search_radius, 
     prm.search_radius = search_radius;
     prm.min_effective_points = 0;
     if ((rc = init_state(ctx, T))) return rc;
-    if ((rc = launch_iteration(ctx, &prm, ctx->d_planes64))) return rc;
+    if ((rc = launch_iteration(ctx, &prm, ctx->d_src, ctx->d_planes64))) return rc;
     double acc[kAcc];
     CK(cudaMemcpyAsync(acc, ctx->d_acc, sizeof(acc), cudaMemcpyDeviceToHost, ctx->stream));
     if (planes_out)
@@ -770,6 +870,8 @@ int dcreg_icp_run(dcreg_ctx* ctx, const dcreg_icp_params* params, const double T
     if (log && log_cap > 0 && (rc = ensure_log(ctx, log_cap))) return rc;
     dcreg_iter_log* dlog = (log && log_cap > 0) ? ctx->d_log : nullptr;
     if ((rc = init_state(ctx, T_init))) return rc;
+    const float4* src_iter = ctx->d_src;
+    if ((rc = sort_source_by_cell(ctx, T_init, &src_iter))) return rc;
     int issued = 0;
     int chunk = 16;
     int status = DCREG_OK;
@@ -778,7 +880,7 @@ int dcreg_icp_run(dcreg_ctx* ctx, const dcreg_icp_params* params, const double T
     while (issued < params->max_iterations) {
         const int todo = (params->max_iterations - issued) < chunk ? (params->max_iterations - issued) : chunk;
         for (int k = 0; k < todo; ++k) {
-            if ((rc = launch_iteration(ctx, params, nullptr))) return rc;
+            if ((rc = launch_iteration(ctx, params, src_iter, nullptr))) return rc;
             if ((rc = nccl_allreduce_acc(ctx))) return rc;          // no-op on one GPU
             k2_step_kernel<<<1, 32, 0, ctx->stream>>>(ctx->d_acc, ctx->d_state, *params, dlog, log_cap);
             ctx->launches++;
@@ -792,6 +894,10 @@ int dcreg_icp_run(dcreg_ctx* ctx, const dcreg_icp_params* params, const double T
             if (*flag) break;
             chunk = 32;
         }
+    }
+    if (dlog) {
+        log_fill_kernel<<<(log_cap + 31) / 32, 32, 0, ctx->stream>>>(dlog, log_cap, ctx->d_state, *params);
+        ctx->launches++;
     }
     if ((rc = read_results(ctx, T_out, log, log_cap, n_iterations, converged, &status))) return rc;
     return status;
@@ -838,6 +944,10 @@ int dcreg_icp_run_host_planes(dcreg_ctx* ctx, const dcreg_icp_params* params, co
         if (hs->done) break;
     }
     int status = DCREG_OK;
+    if (dlog) {
+        log_fill_kernel<<<(log_cap + 31) / 32, 32, 0, ctx->stream>>>(dlog, log_cap, ctx->d_state, *params);
+        ctx->launches++;
+    }
     if ((rc = read_results(ctx, T_out, log, log_cap, n_iterations, converged, &status))) return rc;
     return status;
 }

@@ -1,5 +1,6 @@
-// k1_reduce.cuh - K1: fused point-to-plane residual / weight / 6-DoF Jacobian / normal-equation
-// reduction for sm_100a.
+// k1_reduce.cuh - per-slot math and the Gram-matrix reduction shared by the two producers of the normal
+// equations: the streaming kernel K1 (k1_stream.cuh: frozen planes) and the fused ICP iteration kernel
+// (dcreg_b200.cu: planes come straight out of the correspondence stage).
 //
 // Replaces, per source slot and per ICP iteration (reference file:line):
 //   pointBodyToGlobal (FP64 math, float32 store)         DCReg/include/utils.hpp:630-636
@@ -9,13 +10,14 @@
 //   H = A^T A, g = A^T b                                  icp_test_runner.cpp:1910-1919
 //   SymmetricHessianComputer (21 + 6 accumulators)        DCReg/include/hessian_computer.h:62-123
 //
-// Roofline: HBM.  Algorithmic bytes per slot = 32 (float4 point + float4 plane); 48 with the
-// FP64 plane variant.  All products and sums are FP64 (precision contract: pose 1e-6, Schur
-// eigenvalues 1e-8 relative), so the FP64 pipe (64 FMA/clk/SM) is the second bound: the per-slot
-// FP64 work is cut by accumulating the outer products in the WORLD frame,
-//     J_r = [ (p x R^T n)^T , (R^T n)^T ] = [ (Rp x n)^T , n^T ] * blkdiag(R, R),
-// so the 27 sums are taken over u = [Rp x n ; n] (Rp is a by-product of the point transform) and
-// the constant 6x6 congruence with blkdiag(R,R) is applied once, in the final reduce.
+// Formulation.  The reference's Jacobian row is (s + r ds_dr) [ -n^T R [p]x , n^T R ] with the normal rebuilt
+// from the float32-stored coeff = (s n, s r) as n = coeff/s (:1786-1790, 1889, 1898, 1906).  With u' = fl32(s n)
+// and w = s + r ds_dr this row equals
+//       (w/s) [ (Rp x u')^T , u'^T ] blkdiag(R, R),
+// so per slot only the 8 world-frame components c = [k (Rp x u'), k u', b, r] are formed (k = w/s = 1 without
+// the weight derivative, 2 - 1/s with it; b = -fl32(s r)), the sums are the 8x8 Gram matrix C = sum c c^T
+//       H_world = C[0:6,0:6],  g_world = C[0:6,6],  sum b^2 = C[6,6],  sum r^2 = C[7,7],
+// and the constant congruence with blkdiag(R, R) is applied once, in the last block.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -25,27 +27,13 @@ namespace k1 {
 
 using k2::kAcc;
 
+constexpr int kGramPart = 66;            // per-block partial: 64 Gram entries + N_eff + N_corr_pt
+constexpr int kTRow = 36;                // padded row stride (doubles) of a warp's DMMA transpose buffer
+
 struct Pose {            // R row-major, t
     double R[9];
     double t[3];
 };
-
-struct Acc {
-    double h[21];        // upper triangle of sum a a^T, a = w * u (world frame)
-    double g[6];         // sum a * b
-    double sr2;          // sum r^2 over effective slots          (rmse, icp_test_runner.cpp:1803,1858)
-    double sb2;          // sum b^2                                (objective, icp_test_runner.cpp:1919)
-    int neff;            // effective correspondences
-    int npt;             // correspondence_pt_count (set by the caller of accumulate_slot)
-};
-
-__device__ __forceinline__ void acc_zero(Acc& a) {
-#pragma unroll
-    for (int i = 0; i < 21; ++i) a.h[i] = 0.0;
-#pragma unroll
-    for (int i = 0; i < 6; ++i) a.g[i] = 0.0;
-    a.sr2 = 0.0; a.sb2 = 0.0; a.neff = 0; a.npt = 0;
-}
 
 // fast full-precision reciprocal for s in (0.1, 1]: MUFU.RCP64H seed + 2 Newton steps (error < 1 ulp)
 __device__ __forceinline__ double rcp_newton(double s) {
@@ -57,57 +45,9 @@ __device__ __forceinline__ double rcp_newton(double s) {
     return fma(y, e, y);
 }
 
-// One slot.  (px,py,pz) body-frame point, (nx,ny,nz,d) plane in the world frame (FP64 values;
-// the float4 variants convert before the call).  Weight rule: icp_test_runner.cpp:1776-1785.
-//
-// The reference stores coeff = (s n, s r) as float32 and rebuilds the normal as coeff/s
-// (:1786-1790, 1889, 1906); the Jacobian row is (s + r ds_dr) [ -n^T R [p]x , n^T R ] (:1898).
-// With u' = fl32(s n) this is (w/s) [ (Rp x u')^T , u'^T ] blkdiag(R,R), w = s + r ds_dr, so the 1/s
-// never has to be applied to the three components: w/s = 1 without the weight derivative and
-// 2 - 1/s with it (r ds_dr = -0.9|r| = s - 1 on 0 < s < 1).
-__device__ __forceinline__ void accumulate_slot(Acc& a, const Pose& P, double px, double py, double pz,
-                                                double nx, double ny, double nz, double d, bool use_wd,
-                                                bool has_plane) {
-    // q = fl32(R p + t)  (utils.hpp:630-636: FP64 math, float32 store)
-    const double wx = P.R[0] * px + P.R[1] * py + P.R[2] * pz;   // Rp (world-rotated, no translation)
-    const double wy = P.R[3] * px + P.R[4] * py + P.R[5] * pz;
-    const double wz = P.R[6] * px + P.R[7] * py + P.R[8] * pz;
-    const double qx = (double)(float)(wx + P.t[0]);
-    const double qy = (double)(float)(wy + P.t[1]);
-    const double qz = (double)(float)(wz + P.t[2]);
-    const double r = nx * qx + ny * qy + nz * qz + d;            // icp_test_runner.cpp:1774
-    const double s = 1.0 - 0.9 * fabs(r);                        // :1776 (the max(0, .) is implied by the gate)
-    if (!(has_plane && s > 0.1)) return;                         // :1785
-    const double ux = (double)(float)(s * nx);
-    const double uy = (double)(float)(s * ny);
-    const double uz = (double)(float)(s * nz);
-    const double b = -(double)(float)(s * r);
-    double v[6];
-    v[0] = wy * uz - wz * uy;                                    // Rp x u'
-    v[1] = wz * ux - wx * uz;
-    v[2] = wx * uy - wy * ux;
-    v[3] = ux; v[4] = uy; v[5] = uz;
-    if (use_wd && s < 1.0) {                                     // :1780-1783, 1898
-        const double k = 2.0 - rcp_newton(s);
-#pragma unroll
-        for (int i = 0; i < 6; ++i) v[i] *= k;
-    }
-    int k = 0;
-#pragma unroll
-    for (int i = 0; i < 6; ++i) {
-#pragma unroll
-        for (int j = i; j < 6; ++j) { a.h[k] = fma(v[i], v[j], a.h[k]); ++k; }
-        a.g[i] = fma(v[i], b, a.g[i]);
-    }
-    a.sr2 = fma(r, r, a.sr2);
-    a.sb2 = fma(b, b, a.sb2);
-    a.neff += 1;
-}
-
 // (double)(float)x without the two F2F conversions: round-to-nearest-even to 24 significant bits directly on
-// the FP64 bit pattern (5 integer instructions on the ALU pipe instead of 16 cycles of the 16-lane XU pipe,
-// which profiles showed to be the busiest unit of this kernel).  Identical to the float round trip for
-// x = 0 and for 2^-126 <= |x| < 2^128, i.e. whenever the float32 result is a normal number or zero.
+// the FP64 bit pattern (5 integer instructions).  Identical to the float round trip for x = 0 and for
+// 2^-126 <= |x| < 2^128, i.e. whenever the float32 result is a normal number or zero.
 __device__ __forceinline__ double round_f32(double x) {
     unsigned long long b = (unsigned long long)__double_as_longlong(x);
     const unsigned lsb = ((unsigned)b >> 29) & 1u;
@@ -129,154 +69,174 @@ __device__ __forceinline__ double f32_to_f64(float f) {
     return __hiloint2double((int)hi, (int)(u << 29));
 }
 
-// Branch-free variant for U independent slots handled by one thread (straight-line code, so ptxas
-// interleaves the U dependency chains and hides the XU / FP64 latencies).  Invalid slots (no plane, or
-// weight gate failed) contribute exact zeros: their weight s is forced to 0, which zeroes u', b and the row.
-template <int U, bool kUseWd>
-__device__ __forceinline__ void accumulate_slots(Acc& a, const Pose& P, const double (&px)[U], const double (&py)[U],
-                                                 const double (&pz)[U], const double (&nx)[U], const double (&ny)[U],
-                                                 const double (&nz)[U], const double (&d)[U], const bool (&has)[U]) {
-    double wx[U], wy[U], wz[U], r[U], s[U], b[U], v[U][6];
-    bool valid[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-        wx[u] = P.R[0] * px[u] + P.R[1] * py[u] + P.R[2] * pz[u];
-        wy[u] = P.R[3] * px[u] + P.R[4] * py[u] + P.R[5] * pz[u];
-        wz[u] = P.R[6] * px[u] + P.R[7] * py[u] + P.R[8] * pz[u];
+// Per-slot front: residual, weight, gate, float32 round trips, Jacobian row in the world frame.
+// Output c[8] = [k (Rp x u'), k u', b, r], all zeros for an invalid slot (no plane or gated out).
+template <bool kUseWd>
+__device__ __forceinline__ void slot_front(const Pose& P, double px, double py, double pz, double nx, double ny,
+                                           double nz, double d, bool has, double (&c)[8], int& neff) {
+    const double wx = fma(P.R[2], pz, fma(P.R[1], py, P.R[0] * px));     // Rp (no translation)
+    const double wy = fma(P.R[5], pz, fma(P.R[4], py, P.R[3] * px));
+    const double wz = fma(P.R[8], pz, fma(P.R[7], py, P.R[6] * px));
+    const double qx = round_f32(wx + P.t[0]);                     // utils.hpp:630-636 (float32 store)
+    const double qy = round_f32(wy + P.t[1]);
+    const double qz = round_f32(wz + P.t[2]);
+    const double rr = fma(nx, qx, fma(ny, qy, fma(nz, qz, d)));   // icp_test_runner.cpp:1774
+    const double ss = 1.0 - 0.9 * fabs(rr);                       // :1776 (max(0, .) is implied by the gate)
+    const bool valid = has && (ss > 0.1);                         // :1785
+    const double s = valid ? ss : 0.0;
+    const double r = valid ? rr : 0.0;
+    double ux = round_f32(s * nx);                                // coeff.x/y/z (:1787-1789)
+    double uy = round_f32(s * ny);
+    double uz = round_f32(s * nz);
+    c[6] = -round_f32(s * r);                                     // -coeff.intensity (:1790, 1906)
+    c[7] = r;
+    if (kUseWd) {                                                 // :1780-1783, 1898: row scale w/s = 2 - 1/s on 0 < s < 1
+        const double sw = valid ? ss : 1.0;                       // (s == 1 gives k = 1: no derivative, as in the reference)
+        const double k = 2.0 - rcp_newton(sw);
+        ux *= k; uy *= k; uz *= k;
     }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-        const double qx = round_f32(wx[u] + P.t[0]);             // utils.hpp:630-636 (float32 store)
-        const double qy = round_f32(wy[u] + P.t[1]);
-        const double qz = round_f32(wz[u] + P.t[2]);
-        const double rr = nx[u] * qx + ny[u] * qy + nz[u] * qz + d[u];   // icp_test_runner.cpp:1774
-        const double ss = 1.0 - 0.9 * fabs(rr);                  // :1776
-        valid[u] = has[u] && (ss > 0.1);                         // :1785
-        s[u] = valid[u] ? ss : 0.0;
-        r[u] = valid[u] ? rr : 0.0;
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-        const double ux = round_f32(s[u] * nx[u]);               // coeff.x/y/z  (:1787-1789)
-        const double uy = round_f32(s[u] * ny[u]);
-        const double uz = round_f32(s[u] * nz[u]);
-        b[u] = -round_f32(s[u] * r[u]);                          // -coeff.intensity (:1790, 1906)
-        v[u][0] = wy[u] * uz - wz[u] * uy;                       // Rp x u'
-        v[u][1] = wz[u] * ux - wx[u] * uz;
-        v[u][2] = wx[u] * uy - wy[u] * ux;
-        v[u][3] = ux; v[u][4] = uy; v[u][5] = uz;
-        if (kUseWd) {                                            // :1780-1783, 1898: row scale w/s = 2 - 1/s on 0 < s < 1
-            const double sw = (valid[u] && s[u] < 1.0) ? s[u] : 1.0;
-            const double k = 2.0 - rcp_newton(sw);
-#pragma unroll
-            for (int i = 0; i < 6; ++i) v[u][i] *= k;
-        }
-        a.neff += valid[u] ? 1 : 0;
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-        int k = 0;
-#pragma unroll
-        for (int i = 0; i < 6; ++i) {
-#pragma unroll
-            for (int j = i; j < 6; ++j) { a.h[k] = fma(v[u][i], v[u][j], a.h[k]); ++k; }
-            a.g[i] = fma(v[u][i], b[u], a.g[i]);
-        }
-        a.sr2 = fma(r[u], r[u], a.sr2);
-        a.sb2 = fma(b[u], b[u], a.sb2);
-    }
+    c[0] = wy * uz - wz * uy;                                     // Rp x (k u')
+    c[1] = wz * ux - wx * uz;
+    c[2] = wx * uy - wy * ux;
+    c[3] = ux; c[4] = uy; c[5] = uz;
+    neff += valid ? 1 : 0;
 }
 
-__device__ __forceinline__ double shfl_down_d(double v, int off) {
-    return __shfl_down_sync(0xffffffffu, v, off);
+// ---- Gram accumulation with the FP64 tensor-core instruction (used by the ICP iteration kernel) -----------------
+// One mma.sync.m8n8k4 (SASS: DMMA) adds c c^T for 4 slots: A = c (8 components x 4 slots), B = A^T; each lane owns
+// only two entries of C (flat index 2*lane, 2*lane + 1), so no per-thread block of 29 accumulators is needed next to
+// the register-hungry k-NN / plane-fit code.  The per-slot components are transposed into the fragment layout
+// through a 2.3 KB per-warp shared buffer (8 STS.64 + 8 LDS.64 per 32 slots, conflict-free with the padded stride).
+// (The streaming kernel uses plain DFMA chains instead: there the FP64 issue slots are the bottleneck and
+// 29 DFMA x 2 cycles beat 8 DMMA x 16.4 cycles.)  All 32 lanes must call this convergently.
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
 }
 
-// Warp tree -> shared staging (one row of kAcc per warp) -> block partial in global memory.
-// smem must hold (blockDim.x/32) * kAcc doubles.  All threads of the block must call this.
-__device__ __forceinline__ void block_reduce_store(const Acc& a, double* smem, double* block_out) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    double vals[k2::kAccUsed];
+__device__ __forceinline__ void gram_accumulate_dmma(double* tb, int lane, const double (&c)[8], double& c0, double& c1,
+                                                     double& e0, double& e1) {
+    const int rd_off = (lane >> 2) * kTRow + (lane & 3);   // fragment element: component lane/4 of slot lane%4
 #pragma unroll
-    for (int i = 0; i < 21; ++i) vals[i] = a.h[i];
+    for (int j = 0; j < 8; ++j) tb[j * kTRow + lane] = c[j];
+    __syncwarp();
 #pragma unroll
-    for (int i = 0; i < 6; ++i) vals[21 + i] = a.g[i];
-    vals[k2::kAccSumR2] = a.sr2;
-    vals[k2::kAccNeff] = (double)a.neff;
-    vals[k2::kAccNpt] = (double)a.npt;
-    vals[k2::kAccSumB2] = a.sb2;
-#pragma unroll
-    for (int i = 0; i < k2::kAccUsed; ++i) {
-        double v = vals[i];
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) v += shfl_down_d(v, off);
-        if (lane == 0) smem[warp * kAcc + i] = v;
+    for (int g = 0; g < 8; g += 2) {
+        const double f0 = tb[rd_off + 4 * g], f1 = tb[rd_off + 4 * g + 4];
+        dmma884(c0, c1, f0, f0);
+        dmma884(e0, e1, f1, f1);                            // two accumulator pairs: halves the dependent chain
     }
+    __syncwarp();
+}
+
+// ---- block / grid reduction of the Gram fragments ---------------------------------------------------------------
+struct GramSmem {
+    double red[8][kGramPart];
+    double fin[kGramPart + 6];
+    bool is_last;
+};
+
+// Every thread of a 256-thread block calls this with its two Gram entries (flat index 2*lane + {0,1} of its warp's
+// 8x8 Gram) and its counters.  Block partial -> global; the last block to arrive (atomic ticket) sums the partials
+// in a fixed order with its 8 warps in parallel, applies the world->body congruence with 42 threads and writes
+// acc_out[kAcc] = 21 upper-triangular entries (hessian_computer.h order) + 6 rhs + {sum r^2, N_eff, N_pt, sum b^2}.
+// Deterministic for a given grid size.
+__device__ __forceinline__ void finish_block(double c0, double c1, int neff, int npt, GramSmem& gs, double* partials,
+                                             unsigned int* counter, const double* R, double* acc_out) {
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        neff += __shfl_down_sync(0xffffffffu, neff, off);
+        npt += __shfl_down_sync(0xffffffffu, npt, off);
+    }
+    gs.red[warp][2 * lane] = c0;
+    gs.red[warp][2 * lane + 1] = c1;
+    if (lane == 0) { gs.red[warp][64] = (double)neff; gs.red[warp][65] = (double)npt; }
     __syncthreads();
-    if (threadIdx.x < k2::kAccUsed) {
+    if (tid < kGramPart) {
         double s = 0.0;
-        for (int w = 0; w < nwarps; ++w) s += smem[w * kAcc + threadIdx.x];
-        block_out[threadIdx.x] = s;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) s += gs.red[w][tid];
+        partials[(size_t)blockIdx.x * kGramPart + tid] = s;
     }
-}
-
-// Congruence with Q = blkdiag(R,R): H_body = Q^T H_world Q, g_body = Q^T g_world.
-// in/out: 27 packed values (21 upper + 6 rhs).  Single thread.
-__device__ inline void world_to_body(double* v27, const double* R) {
-    double H[36], g[6], T[36], Hb[36], gb[6];
-    k2::unpack_H(v27, H, g);
-    // T = H * Q  (columns in blocks: T[:, 0:3] = H[:, 0:3] R, T[:, 3:6] = H[:, 3:6] R)
-    for (int i = 0; i < 6; ++i)
-        for (int blk = 0; blk < 2; ++blk)
-            for (int j = 0; j < 3; ++j) {
-                double s = 0.0;
-                for (int k = 0; k < 3; ++k) s += H[i * 6 + blk * 3 + k] * R[k * 3 + j];
-                T[i * 6 + blk * 3 + j] = s;
-            }
-    // Hb = Q^T * T
-    for (int blk = 0; blk < 2; ++blk)
-        for (int i = 0; i < 3; ++i)
-            for (int j = 0; j < 6; ++j) {
-                double s = 0.0;
-                for (int k = 0; k < 3; ++k) s += R[k * 3 + i] * T[(blk * 3 + k) * 6 + j];
-                Hb[(blk * 3 + i) * 6 + j] = s;
-            }
-    for (int blk = 0; blk < 2; ++blk)
-        for (int i = 0; i < 3; ++i) {
-            double s = 0.0;
-            for (int k = 0; k < 3; ++k) s += R[k * 3 + i] * g[blk * 3 + k];
-            gb[blk * 3 + i] = s;
-        }
-    int k = 0;
-    for (int i = 0; i < 6; ++i)
-        for (int j = i; j < 6; ++j) v27[k++] = 0.5 * (Hb[i * 6 + j] + Hb[j * 6 + i]);
-    for (int i = 0; i < 6; ++i) v27[21 + i] = gb[i];
-}
-
-// Last-block final reduce: sums the per-block partials in block order (deterministic), applies
-// the world->body congruence, writes acc_out[kAcc].  Called by every thread of the LAST block.
-__device__ __forceinline__ void final_reduce(const double* partials, int nblocks, const double* R,
-                                             double* smem, double* acc_out) {
-    // thread i < kAccUsed sums column i over blocks with 4 independent chains
-    if (threadIdx.x < k2::kAccUsed) {
-        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-        int b = 0;
-        for (; b + 3 < nblocks; b += 4) {
-            s0 += __ldcg(&partials[(b + 0) * kAcc + threadIdx.x]);
-            s1 += __ldcg(&partials[(b + 1) * kAcc + threadIdx.x]);
-            s2 += __ldcg(&partials[(b + 2) * kAcc + threadIdx.x]);
-            s3 += __ldcg(&partials[(b + 3) * kAcc + threadIdx.x]);
-        }
-        for (; b < nblocks; ++b) s0 += __ldcg(&partials[b * kAcc + threadIdx.x]);
-        smem[threadIdx.x] = (s0 + s1) + (s2 + s3);
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        const unsigned int tk = atomicAdd(counter, 1u);
+        gs.is_last = (tk == gridDim.x - 1);
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        double v[kAcc];
-        for (int i = 0; i < k2::kAccUsed; ++i) v[i] = smem[i];
-        v[kAcc - 1] = 0.0;
-        world_to_body(v, R);
-        for (int i = 0; i < kAcc; ++i) acc_out[i] = v[i];
+    if (!gs.is_last) return;
+    __threadfence();
+    {
+        const int nb = (int)gridDim.x;
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0;                     // elements lane, lane + 32, lane + 64 (< kGramPart)
+        int b = warp;
+        for (; b + 24 < nb; b += 32) {                           // warp w sums blocks w, w+8, ...; 4 blocks per trip
+            double t0[4], t1[4], t2[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const double* row = partials + (size_t)(b + u * 8) * kGramPart;
+                t0[u] = __ldcg(row + lane);
+                t1[u] = __ldcg(row + 32 + lane);
+                t2[u] = (lane < kGramPart - 64) ? __ldcg(row + 64 + lane) : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { s0 += t0[u]; s1 += t1[u]; s2 += t2[u]; }
+        }
+        for (; b < nb; b += 8) {
+            const double* row = partials + (size_t)b * kGramPart;
+            s0 += __ldcg(row + lane);
+            s1 += __ldcg(row + 32 + lane);
+            if (lane < kGramPart - 64) s2 += __ldcg(row + 64 + lane);
+        }
+        __syncthreads();                                          // red[][] is free again
+        gs.red[warp][lane] = s0;
+        gs.red[warp][32 + lane] = s1;
+        if (lane < kGramPart - 64) gs.red[warp][64 + lane] = s2;
     }
+    __syncthreads();
+    double* fin = gs.fin;
+    if (tid < kGramPart) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) s += gs.red[w][tid];
+        fin[tid] = s;
+    }
+    __syncthreads();
+    // Gram (world frame) -> H_body = Q^T H Q, g_body = Q^T g with Q = blkdiag(R, R): one thread per output entry
+    double* outv = &gs.red[0][0];
+    if (tid < 36) {
+        const int i = tid / 6, j = tid % 6;
+        if (j >= i) {
+            const int bi = (i / 3) * 3, bj = (j / 3) * 3, ii = i % 3, jj = j % 3;
+            double acc = 0.0;
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+#pragma unroll
+                for (int l = 0; l < 3; ++l) {
+                    const double h = 0.5 * (fin[(bi + k) * 8 + bj + l] + fin[(bj + l) * 8 + bi + k]);
+                    acc = fma(R[k * 3 + ii] * h, R[l * 3 + jj], acc);
+                }
+            outv[i * 6 - (i * (i - 1)) / 2 + (j - i)] = acc;      // packed upper-triangular index, row-major
+        }
+    } else if (tid < 42) {
+        const int i = tid - 36, bi = (i / 3) * 3, ii = i % 3;
+        double acc = 0.0;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) acc = fma(R[k * 3 + ii], 0.5 * (fin[(bi + k) * 8 + 6] + fin[6 * 8 + bi + k]), acc);
+        outv[21 + i] = acc;
+    } else if (tid == 42) {
+        outv[k2::kAccSumR2] = fin[7 * 8 + 7];
+        outv[k2::kAccNeff] = fin[64];
+        outv[k2::kAccNpt] = fin[65];
+        outv[k2::kAccSumB2] = fin[6 * 8 + 6];
+        outv[kAcc - 1] = 0.0;
+    }
+    __syncthreads();
+    if (tid < kAcc) acc_out[tid] = outv[tid];
+    if (tid == 0) *counter = 0u;
 }
 
 }  // namespace k1

@@ -115,11 +115,20 @@ __device__ inline void qr6(const double* H, const double* g, double* x) {
 }
 
 // analysis + solve for one 6x6 system.  Single thread.
+// kFull = true : everything DegeneracyAnalysisResult holds (the host-callable seam, and the post-run log fill).
+// kFull = false: only what the chosen (detection, handling) pair needs to produce dx - the per-iteration critical
+//                path of the loop; the log-only quantities (full EVD/SVD, diagonal blocks, alignment report, and the
+//                Schur blocks when the method does not use them) are filled after the run, one thread per iteration.
+template <bool kFull>
 __device__ inline void analyze_and_solve(const double* v27, const dcreg_icp_params& prm,
                                          dcreg_analysis* a, double* dx) {
     double H[36], g[6];
     unpack_H(v27, H, g);
     const double NaN = nan("");
+    const bool need_evd6 = kFull || prm.detection == DCREG_DET_FULL_EVD_MIN_EIGENVALUE ||
+                           prm.detection == DCREG_DET_FULL_SVD_CONDITION ||
+                           prm.handling == DCREG_HAND_SOLUTION_REMAPPING || prm.handling == DCREG_HAND_TRUNCATED_SVD;
+    const bool need_schur = kFull || prm.detection == DCREG_DET_SCHUR_CONDITION_NUMBER;
 
     // ---- defaults of DegeneracyAnalysisResult (utils.hpp:427-448) ----
     a->is_degenerate = 0; a->pcg_iterations = 0; a->pcg_residual = 0.0;
@@ -134,8 +143,12 @@ __device__ inline void analyze_and_solve(const double* v27, const dcreg_icp_para
 
     // ---- full EVD / "SVD" of H (dcreg.hpp:62-89) ----
     double W[36], lam[6], V[36];
-    for (int i = 0; i < 36; ++i) W[i] = H[i];
-    dla::jacobi_eigh<6>(W, lam, V);
+    if (need_evd6) {
+        for (int i = 0; i < 36; ++i) W[i] = H[i];
+        dla::jacobi_eigh<6>(W, lam, V);
+    } else {
+        for (int i = 0; i < 6; ++i) lam[i] = NaN;
+    }
     for (int i = 0; i < 6; ++i) a->eigenvalues_full[i] = lam[i];
     a->cond_full_sub_trans = fabs(lam[2]) / fmax(fabs(lam[0]), 1e-12);
     a->cond_full_sub_rot = fabs(lam[5]) / fmax(fabs(lam[3]), 1e-12);
@@ -152,6 +165,7 @@ __device__ inline void analyze_and_solve(const double* v27, const dcreg_icp_para
     for (int i = 0; i < 6; ++i) a->singular_values[i] = fabs(lam[order[i]]);
     a->cond_full = (a->singular_values[5] > 1e-12) ? a->singular_values[0] / a->singular_values[5]
                                                    : (double)INFINITY;
+    if (!need_evd6) a->cond_full = NaN;
 
     // ---- diagonal blocks + Schur complements (icp_test_runner.cpp:2418-2469, paper Eq. 18) ----
     double HRR[9], Htt[9], HRt[9], HtR[9];
@@ -163,20 +177,29 @@ __device__ inline void analyze_and_solve(const double* v27, const dcreg_icp_para
             HtR[i * 3 + j] = H[(i + 3) * 6 + j];
         }
     double tmpA[9], tmpV[9];
-    for (int i = 0; i < 9; ++i) tmpA[i] = HRR[i];
-    dla::jacobi_eigh<3>(tmpA, a->lambda_sub_rot, tmpV);
-    for (int i = 0; i < 9; ++i) tmpA[i] = Htt[i];
-    dla::jacobi_eigh<3>(tmpA, a->lambda_sub_trans, tmpV);
-    a->cond_diag_rot = cond3(a->lambda_sub_rot);
-    a->cond_diag_trans = cond3(a->lambda_sub_trans);
+    if (kFull) {
+        dla::jacobi_eigh3(HRR, a->lambda_sub_rot, tmpV);
+        dla::jacobi_eigh3(Htt, a->lambda_sub_trans, tmpV);
+        a->cond_diag_rot = cond3(a->lambda_sub_rot);
+        a->cond_diag_trans = cond3(a->lambda_sub_trans);
+    } else {
+        for (int i = 0; i < 3; ++i) a->lambda_sub_rot[i] = a->lambda_sub_trans[i] = NaN;
+        a->cond_diag_rot = a->cond_diag_trans = NaN;
+    }
 
     double HttInv[9], HRRInv[9];
-    for (int i = 0; i < 9; ++i) tmpA[i] = Htt[i];
-    const bool ok_t = dla::fullpiv_inverse<3>(tmpA, HttInv);
-    for (int i = 0; i < 9; ++i) tmpA[i] = HRR[i];
-    const bool ok_r = dla::fullpiv_inverse<3>(tmpA, HRRInv);
-    bool schur_ok = ok_t && ok_r;
-    if (schur_ok) {
+    bool schur_ok = false;
+    if (need_schur) {
+        for (int i = 0; i < 9; ++i) tmpA[i] = Htt[i];
+        const bool ok_t = dla::fullpiv_inverse<3>(tmpA, HttInv);
+        for (int i = 0; i < 9; ++i) tmpA[i] = HRR[i];
+        const bool ok_r = dla::fullpiv_inverse<3>(tmpA, HRRInv);
+        schur_ok = ok_t && ok_r;
+    }
+    if (!need_schur) {
+        for (int i = 0; i < 3; ++i) a->lambda_schur_rot[i] = a->lambda_schur_trans[i] = NaN;
+        a->cond_schur_rot = a->cond_schur_trans = NaN;
+    } else if (schur_ok) {
         double T1[9], T2[9], SR[9], St[9];
         dla::mat3_mul(HRt, HttInv, T1); dla::mat3_mul(T1, HtR, T2);
         for (int i = 0; i < 9; ++i) SR[i] = HRR[i] - T2[i];
@@ -188,12 +211,14 @@ __device__ inline void analyze_and_solve(const double* v27, const dcreg_icp_para
                 const double m1 = 0.5 * (SR[i * 3 + j] + SR[j * 3 + i]); SR[i * 3 + j] = SR[j * 3 + i] = m1;
                 const double m2 = 0.5 * (St[i * 3 + j] + St[j * 3 + i]); St[i * 3 + j] = St[j * 3 + i] = m2;
             }
-        dla::jacobi_eigh<3>(SR, a->lambda_schur_rot, a->schur_V_rot);
-        dla::jacobi_eigh<3>(St, a->lambda_schur_trans, a->schur_V_trans);
+        dla::jacobi_eigh3(SR, a->lambda_schur_rot, a->schur_V_rot);
+        dla::jacobi_eigh3(St, a->lambda_schur_trans, a->schur_V_trans);
         a->cond_schur_rot = cond3(a->lambda_schur_rot);
         a->cond_schur_trans = cond3(a->lambda_schur_trans);
-        align_axes(a->schur_V_rot, a->aligned_V_rot, a->rot_indices);
-        align_axes(a->schur_V_trans, a->aligned_V_trans, a->trans_indices);
+        if (kFull) {
+            align_axes(a->schur_V_rot, a->aligned_V_rot, a->rot_indices);
+            align_axes(a->schur_V_trans, a->aligned_V_trans, a->trans_indices);
+        }
     } else {
         for (int i = 0; i < 3; ++i) a->lambda_schur_rot[i] = a->lambda_schur_trans[i] = NaN;
         a->cond_schur_rot = a->cond_schur_trans = (double)INFINITY;
@@ -356,7 +381,7 @@ __device__ inline void icp_step(const double* acc, IcpState* st, const dcreg_icp
         return;
     }
     double dx[6];
-    analyze_and_solve(acc, prm, an, dx);
+    analyze_and_solve<false>(acc, prm, an, dx);
     bool finite = true;
     for (int i = 0; i < 6; ++i) finite = finite && isfinite(dx[i]);
     const double fitness = st->n_source_total > 0 ? (double)n_pt / (double)st->n_source_total : 0.0;

@@ -85,6 +85,63 @@ __device__ inline void jacobi_eigh(double* A, double* w, double* V) {
     }
 }
 
+// 3x3 specialisation kept entirely in registers (all indices static after unrolling): this one sits on the
+// critical path of every ICP iteration (two Schur blocks), the generic version above spills to local memory.
+__device__ inline void jacobi_eigh3(const double* Ain, double* w, double* V) {
+    double a[3][3], v[3][3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) { a[i][j] = Ain[i * 3 + j]; v[i][j] = (i == j) ? 1.0 : 0.0; }
+    for (int sweep = 0; sweep < 40; ++sweep) {
+        const double off = a[0][1] * a[0][1] + a[0][2] * a[0][2] + a[1][2] * a[1][2];
+        const double diag = a[0][0] * a[0][0] + a[1][1] * a[1][1] + a[2][2] * a[2][2];
+        if (off <= 1e-34 * diag || off == 0.0) break;
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+#pragma unroll
+            for (int q = p + 1; q < 3; ++q) {
+                const double apq = a[p][q];
+                if (fabs(apq) < 1e-300) { a[p][q] = a[q][p] = 0.0; continue; }
+                const double app = a[p][p], aqq = a[q][q];
+                const double theta = (aqq - app) / (2.0 * apq);
+                const double tt = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                const double c = 1.0 / sqrt(tt * tt + 1.0), sn = tt * c;
+                const double tau = sn / (1.0 + c);
+                a[p][p] = app - tt * apq;
+                a[q][q] = aqq + tt * apq;
+                a[p][q] = a[q][p] = 0.0;
+                const int k = 3 - p - q;                    // the one remaining index
+                const double akp = a[k][p], akq = a[k][q];
+                a[k][p] = a[p][k] = akp - sn * (akq + tau * akp);
+                a[k][q] = a[q][k] = akq + sn * (akp - tau * akq);
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                    const double vrp = v[r][p], vrq = v[r][q];
+                    v[r][p] = vrp - sn * (vrq + tau * vrp);
+                    v[r][q] = vrq + sn * (vrp - tau * vrq);
+                }
+            }
+        }
+    }
+    double l0 = a[0][0], l1 = a[1][1], l2 = a[2][2];
+    // sort ascending with column swaps (3-element network)
+#define DLA_SWAP3(x, y, cx, cy)                                              \
+    if (y < x) {                                                              \
+        const double t_ = x; x = y; y = t_;                                   \
+        _Pragma("unroll") for (int r = 0; r < 3; ++r) { const double u_ = v[r][cx]; v[r][cx] = v[r][cy]; v[r][cy] = u_; } \
+    }
+    DLA_SWAP3(l0, l1, 0, 1)
+    DLA_SWAP3(l1, l2, 1, 2)
+    DLA_SWAP3(l0, l1, 0, 1)
+#undef DLA_SWAP3
+    w[0] = l0; w[1] = l1; w[2] = l2;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) V[i * 3 + j] = v[i][j];
+}
+
 // ---------------------------------------------------------------------------------------------
 // Least-squares / linear solve by Householder QR with column pivoting, M x N (M >= N), one rhs.
 // Same structure as a rank-revealing pivoted QR solve: columns whose remaining norm falls below
