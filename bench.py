@@ -119,32 +119,38 @@ def c2_params(default_params):
 # ------------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the oracle port on host cores
 # ------------------------------------------------------------------------------------------------
-def cpu_icp_sample(n_points, iters, seed):
-    """Time `iters` full ICP iterations of the oracle on the C2 scene.  Returns (seconds, cores, kind)."""
+_CPU_SCENE = {}
+
+
+def cpu_icp_sample(n_points, iters, seed, thread_mode=1):
+    """Time `iters` full ICP iterations of the C/OpenMP oracle (the port of the reference loop) on the C2 scene,
+    kd-tree build excluded as in the reference's own timing (icp_test_runner.cpp:408-461).
+    thread_mode 1 = all host threads (correspondences + 27-sum reduction), 0 = reference-faithful (8 threads on
+    correspondences only, serial Jacobian build and A^T A).  Returns (seconds, threads, kind)."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import dcreg_oracle_c as oc
     from dcreg_b200.scenes import make_cylinder, g2_initial_pose
-    pts = make_cylinder(n_points, seed=seed)
-    T0 = g2_initial_pose()
-    try:
-        import dcreg_oracle_c as oc          # C/OpenMP port (oracle/dcreg_oracle.c), all host cores
-        if oc.available():
-            return oc.time_icp(pts, pts, T0, iters) + ("port",)
-    except ImportError:
-        pass
-    import dcreg_oracle as o
-    prm = o.Params(max_iterations=iters, conv_rot=0.0, conv_trans=0.0, kappa_target=10.0, use_weight_derivative=True)
-    tree = o.build_tree(pts)                  # kd-tree build is outside the reference's timed region too
+    key = (n_points, seed)
+    if key not in _CPU_SCENE:
+        pts = make_cylinder(n_points, seed=seed)
+        _CPU_SCENE[key] = (pts, oc.Scene(pts, pts))
+    pts, sc = _CPU_SCENE[key]
+    prm = oc.make_params(max_iterations=iters, fixed_iterations=True, kappa_target=10.0, use_weight_derivative=True,
+                         thread_mode=thread_mode)
     t0 = time.perf_counter()
-    o.icp_so3(pts, pts, T0, prm, tree)
-    return time.perf_counter() - t0, 1, "port"
+    st, conv, n_it, T, _ = sc.icp_run(prm, g2_initial_pose(), want_log=False)
+    dt = time.perf_counter() - t0
+    assert st == 0 and n_it == iters
+    return dt, (8 if thread_mode == 0 else oc.max_threads()), "port"
 
 
 def run_reference(args, rank, world):
+    """The reference's own CPU algorithm (oracle port) on the host cores; rank 0 only."""
     if rank != 0:
         return
-    sample_iters = 3
-    for _ in range(max(0, min(args.warmup, 1))):
-        cpu_icp_sample(C2_POINTS, 1, 42)
+    sample_iters = 10
+    for _ in range(max(0, min(args.warmup, 2))):
+        cpu_icp_sample(C2_POINTS, 2, 42)
     times = []
     cores = 1
     for _ in range(max(1, args.steps)):
@@ -152,14 +158,18 @@ def run_reference(args, rank, world):
         times.append(sec)
     tot = float(np.sum(times))
     value = sample_iters * len(times) / tot
+    sec0, cores0, _ = cpu_icp_sample(C2_POINTS, 5, 42, thread_mode=0)
     line = {
         "impl": "reference", "metric": "icp_iterations_per_s", "value": value, "unit": "ICP iterations/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot / len(times),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"C2 synthetic cylinder pair {C2_POINTS} pts, Ours (Schur+PCG), search_radius 1.0",
-                   "sample": f"{sample_iters} ICP iterations per step"},
+        "config": {"workload": f"C2 synthetic cylinder pair {C2_POINTS} pts, method Ours (Schur detection + PCG), "
+                               "search_radius 1.0; CPU port of the reference loop (reference binary not buildable here)",
+                   "sample": f"{sample_iters} ICP iterations per step (the GPU arm runs {C2_ITERS} per step)"},
         "cpu_baseline": {"value": value, "unit": "ICP iterations/s", "cores": cores, "kind": "port",
-                         "sample": f"{sample_iters} iterations x {len(times)} steps of the C2 workload"},
+                         "sample": f"{sample_iters} iterations x {len(times)} steps of the C2 workload, all host threads",
+                         "reference_faithful_8_threads": {"value": 5 / sec0, "cores": cores0,
+                                                          "note": "omp num_threads(8) on correspondences only, serial J build and A^T A (icp_test_runner.cpp:1714,1863-1915)"}},
         "e2e": {"value": value, "unit": "ICP iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -277,9 +287,15 @@ def run_ours(args, rank, local_rank, world):
     # ---------------- CPU baseline (rank 0, N = 1 only) ----------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        sec, cores, kind = cpu_icp_sample(C2_POINTS, 3, 42)
-        cpu = {"value": 3 / sec, "unit": "ICP iterations/s", "cores": cores, "kind": kind,
-               "sample": "3 ICP iterations of the C2 workload (kd-tree build excluded, as in the reference)"}
+        sec, cores, kind = cpu_icp_sample(C2_POINTS, 3, 42)                 # calibrate
+        it_all = int(min(400, max(10, 12.0 / (sec / 3))))                    # ~12 s of CPU work
+        sec, cores, kind = cpu_icp_sample(C2_POINTS, it_all, 42)
+        it_ref = int(min(200, max(5, it_all // 3)))
+        sec0, cores0, _ = cpu_icp_sample(C2_POINTS, it_ref, 42, thread_mode=0)
+        cpu = {"value": it_all / sec, "unit": "ICP iterations/s", "cores": cores, "kind": kind,
+               "sample": f"{it_all} ICP iterations of the C2 workload, all host threads (kd-tree build excluded, as in the reference)",
+               "reference_faithful_8_threads": {"value": it_ref / sec0, "cores": cores0, "sample": f"{it_ref} iterations",
+                                                "note": "omp num_threads(8) on correspondences only, serial J build and A^T A"}}
 
     if rank == 0:
         line = {

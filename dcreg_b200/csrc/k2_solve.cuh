@@ -46,7 +46,7 @@ __device__ inline double cond3(const double* lam) {   // lambda ascending
 
 // paper Alg. 2 (log only): greedy assignment of eigenvectors to the reference axes, sign fix,
 // Gram-Schmidt in slot order.  indices[j] = column of V_raw that landed in slot j.
-__device__ inline void align_axes(const double* V, double* Va, int* indices) {
+__device__ __noinline__ void align_axes(const double* V, double* Va, int* indices) {
     bool used_v[3] = {false, false, false}, used_e[3] = {false, false, false};
     for (int round = 0; round < 3; ++round) {
         double best = -1.0; int bi = 0, bj = 0;
@@ -75,7 +75,7 @@ __device__ inline void align_axes(const double* V, double* Va, int* indices) {
 
 // PCG on H x = g, x0 = 0 (paper Alg. 3; stub DCReg::solvePCG dcreg.hpp:279-287).
 // Stops when ||r||_2 < tol or after max_iter iterations.  Returns iterations used.
-__device__ inline int pcg6(const double* H, const double* g, const double* P, int max_iter,
+__device__ __noinline__ int pcg6(const double* H, const double* g, const double* P, int max_iter,
                            double tol, double* x, double* res_out) {
     double r[6], z[6], p[6], Hp[6];
     for (int i = 0; i < 6; ++i) { x[i] = 0.0; r[i] = g[i]; }
@@ -107,7 +107,7 @@ __device__ inline int pcg6(const double* H, const double* g, const double* P, in
     return it;
 }
 
-__device__ inline void qr6(const double* H, const double* g, double* x) {
+__device__ __noinline__ void qr6(const double* H, const double* g, double* x) {
     double A[36], b[6];
     for (int i = 0; i < 36; ++i) A[i] = H[i];
     for (int i = 0; i < 6; ++i) b[i] = g[i];
@@ -328,7 +328,7 @@ __device__ inline void analyze_and_solve(const double* v27, const dcreg_icp_para
 }
 
 // R <- R exp(w), t <- t + R_old v  (math_utils.hpp:158-166, 20-33)
-__device__ inline void boxplus(double* R, double* t, const double* dx) {
+__device__ __noinline__ void boxplus(double* R, double* t, const double* dx) {
     const double wx = dx[0], wy = dx[1], wz = dx[2];
     const double theta = sqrt(wx * wx + wy * wy + wz * wz);
     double E[9];

@@ -21,7 +21,7 @@ namespace dla {
 // of 1e3..1e6 and the contract is 1e-8 relative on every eigenvalue (SURVEY.md §7 hard parts).
 // ---------------------------------------------------------------------------------------------
 template <int N>
-__device__ inline void jacobi_eigh(double* A, double* w, double* V) {
+__device__ __noinline__ void jacobi_eigh(double* A, double* w, double* V) {
 #pragma unroll
     for (int i = 0; i < N; ++i)
 #pragma unroll
@@ -87,7 +87,7 @@ __device__ inline void jacobi_eigh(double* A, double* w, double* V) {
 
 // 3x3 specialisation kept entirely in registers (all indices static after unrolling): this one sits on the
 // critical path of every ICP iteration (two Schur blocks), the generic version above spills to local memory.
-__device__ inline void jacobi_eigh3(const double* Ain, double* w, double* V) {
+__device__ __noinline__ void jacobi_eigh3(const double* Ain, double* w, double* V) {
     double a[3][3], v[3][3];
 #pragma unroll
     for (int i = 0; i < 3; ++i)
@@ -252,7 +252,7 @@ __device__ inline void colpiv_qr_solve(double* A, double* b, double* x) {
 // A row-major, destroyed; Ainv row-major.
 // ---------------------------------------------------------------------------------------------
 template <int N>
-__device__ inline bool fullpiv_inverse(double* A, double* Ainv) {
+__device__ __noinline__ bool fullpiv_inverse(double* A, double* Ainv) {
     int prow[N], pcol[N];
     double maxpivot = 0.0;
     bool singular = false;
