@@ -270,23 +270,47 @@ __device__ __forceinline__ void knn_scan_range(const float4* __restrict__ pts, i
     }
 }
 
+// distance from coordinate v (inside cell c) to the cell c + dc along one axis: 0 for the own cell
+__device__ __forceinline__ float axis_gap(float v, int c, int dc, float cell) {
+    if (dc == 0) return 0.0f;
+    const float lo = (float)c * cell;
+    return dc < 0 ? (v - lo) : ((lo + cell) - v);
+}
+
 __device__ __forceinline__ void knn_search(const Grid& g, float qx, float qy, float qz, Knn5& k) {
     const int cx = cell_coord(qx, g.inv_cell), cy = cell_coord(qy, g.inv_cell), cz = cell_coord(qz, g.inv_cell);
     if (g.dense) {
-        const int x0 = max(cx - 1 - g.ox, 0), x1 = min(cx + 1 - g.ox, g.nx - 1);
-        if (x0 > x1) return;
-        // gather the 9 row ranges first (independent loads), then scan them
-        int rs[9], re[9];
+        // Row order: own row first, then the 4 face rows, then the 4 edge rows; inside a row the own cell first.
+        // A cell (or a whole row) is skipped when the box distance to it already exceeds the current 5th-best
+        // distance (strictly, with a 1e-5 relative safety margin for the float arithmetic of the bound), which
+        // keeps the search exact: no skipped cell can hold a point that would enter the result.
+        // The loops are deliberately NOT unrolled: one copy of the scan loop keeps the kernel inside the
+        // instruction cache (the fully unrolled version stalled on instruction fetch, profiles/icp_r3).
+        const float cell = (float)(1.0 / g.inv_cell);
+        const int lx = cx - g.ox, ly = cy - g.oy, lz = cz - g.oz;
+        if (lx + 1 < 0 || lx - 1 >= g.nx) return;
+        const float gx[3] = {axis_gap(qx, cx, -1, cell), 0.0f, axis_gap(qx, cx, +1, cell)};
+        const unsigned long long order = 0x862075314ull;       // rows r = (dz+1)*3 + (dy+1) in visiting order 4,1,3,5,7,0,2,6,8
+#pragma unroll 1
+        for (int o = 0; o < 9; ++o) {
+            const int r = (int)((order >> (4 * o)) & 0xF);
+            const int dy = (r % 3) - 1, dz = (r / 3) - 1;
+            const int yy = ly + dy, zz = lz + dz;
+            if (yy < 0 || yy >= g.ny || zz < 0 || zz >= g.nz) continue;
+            const float gy = axis_gap(qy, cy, dy, cell), gz = axis_gap(qz, cz, dz, cell);
+            const float row_lb = (gy * gy + gz * gz) * 0.99999f;
+            if (row_lb > k.d2[4]) continue;
+            const int* rowp = g.cell_start + (size_t)(zz * g.ny + yy) * g.nx;
+            int cs[4];
 #pragma unroll
-        for (int r = 0; r < 9; ++r) {
-            const int yy = cy - g.oy + (r % 3) - 1, zz = cz - g.oz + (r / 3) - 1;
-            const bool ok = (yy >= 0) && (yy < g.ny) && (zz >= 0) && (zz < g.nz);
-            const int row = (zz * g.ny + yy) * g.nx;
-            rs[r] = ok ? __ldg(&g.cell_start[row + x0]) : 0;
-            re[r] = ok ? __ldg(&g.cell_start[row + x1 + 1]) : 0;
+            for (int j = 0; j < 4; ++j) cs[j] = __ldg(rowp + min(max(lx - 1 + j, 0), g.nx));   // x = nx is the row end
+#pragma unroll 1
+            for (int c = 0; c < 3; ++c) {
+                const int col = (c == 0) ? 1 : (c == 1 ? 0 : 2);                             // own column first
+                if (col != 1 && (row_lb + gx[col] * gx[col] * 0.99999f) > k.d2[4]) continue;
+                knn_scan_range(g.pts, cs[col], cs[col + 1], qx, qy, qz, k);
+            }
         }
-#pragma unroll
-        for (int r = 0; r < 9; ++r) knn_scan_range(g.pts, rs[r], re[r], qx, qy, qz, k);
     } else {
         for (int dz = -1; dz <= 1; ++dz)
             for (int dy = -1; dy <= 1; ++dy)
@@ -310,13 +334,13 @@ __device__ __forceinline__ void knn_search(const Grid& g, float qx, float qy, fl
 // Returns true and (n, d) when a valid plane exists.
 __device__ __forceinline__ bool fit_plane(const Grid& g, const Knn5& k, double min_norm, double thickness,
                                           double& nx, double& ny, double& nz, double& d) {
-    double A[15], A0[15], b[5], x[3];
+    double A[15], b[5], x[3];
 #pragma unroll
     for (int j = 0; j < 5; ++j) {
         const float4 p = __ldg(&g.pts[k.pos[j]]);
-        A0[j * 3 + 0] = A[j * 3 + 0] = (double)p.x;
-        A0[j * 3 + 1] = A[j * 3 + 1] = (double)p.y;
-        A0[j * 3 + 2] = A[j * 3 + 2] = (double)p.z;
+        A[j * 3 + 0] = (double)p.x;
+        A[j * 3 + 1] = (double)p.y;
+        A[j * 3 + 2] = (double)p.z;
         b[j] = -1.0;
     }
     dla::colpiv_qr_solve<5, 3>(A, b, x);
@@ -326,7 +350,8 @@ __device__ __forceinline__ bool fit_plane(const Grid& g, const Knn5& k, double m
     double worst = 0.0;
 #pragma unroll
     for (int j = 0; j < 5; ++j) {
-        double e = nx * A0[j * 3 + 0] + ny * A0[j * 3 + 1] + nz * A0[j * 3 + 2] + d;
+        const float4 p = __ldg(&g.pts[k.pos[j]]);         // re-read (L1 hit) instead of holding 15 more doubles
+        double e = nx * (double)p.x + ny * (double)p.y + nz * (double)p.z + d;
         e *= e;
         worst = fmax(worst, e);
     }

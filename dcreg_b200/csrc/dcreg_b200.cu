@@ -80,7 +80,7 @@ struct IterSmem {
 // the residual / weight / Jacobian row and the Gram accumulation (S4-S5).  One source point per thread per trip;
 // no per-thread accumulator block: the 8x8 Gram is accumulated with DMMA (two registers per lane).
 template <bool kUseWd>
-__global__ void __launch_bounds__(kBlock, 2) icp_iteration_kernel(const __grid_constant__ IterArgs a) {
+__global__ void __launch_bounds__(kBlock, 3) icp_iteration_kernel(const __grid_constant__ IterArgs a) {
     __shared__ IterSmem sm;
     if (a.state->done) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;

@@ -153,7 +153,7 @@ __device__ __noinline__ void jacobi_eigh3(const double* Ain, double* w, double* 
 // H.colPivHouseholderQr().solve(g) (dcreg.hpp:182,190,197).
 // ---------------------------------------------------------------------------------------------
 template <int M, int N>
-__device__ inline void colpiv_qr_solve(double* A, double* b, double* x) {
+__device__ __noinline__ void colpiv_qr_solve(double* A, double* b, double* x) {
     const double eps = 2.220446049250313e-16;
     double normU[N], normD[N];
     int perm[N];

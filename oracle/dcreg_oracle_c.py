@@ -109,10 +109,10 @@ def max_threads() -> int:
 
 
 def time_icp(src, tgt, T0, iters, thread_mode=1):
-    """Seconds for `iters` fixed ICP iterations ("Ours", weight derivative on), kd-tree build excluded.
+    """Seconds for `iters` fixed ICP iterations ("Ours", released defaults), kd-tree build excluded.
     Returns (seconds, threads_used)."""
     sc = Scene(src, tgt)
-    prm = make_params(max_iterations=iters, fixed_iterations=True, kappa_target=10.0, use_weight_derivative=True,
+    prm = make_params(max_iterations=iters, fixed_iterations=True, kappa_target=10.0, use_weight_derivative=False,
                       thread_mode=thread_mode)
     t0 = time.perf_counter()
     sc.icp_run(prm, T0, want_log=False)

@@ -11,7 +11,7 @@ pts = make_cylinder(n, seed=42)
 with Context(0) as ctx:
     ctx.set_target(pts, 1.0)
     ctx.set_source(pts)
-    prm = default_params(max_iterations=iters, fixed_iterations=1, kappa_target=10.0, use_weight_derivative=1)
+    prm = default_params(max_iterations=iters, fixed_iterations=1, kappa_target=10.0, use_weight_derivative=int(os.environ.get("ICP_WD", "0")))
     for _ in range(2):
         t0 = time.perf_counter()
         res = ctx.icp_run(prm, g2_initial_pose(), want_log=False)
