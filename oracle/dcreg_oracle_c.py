@@ -52,6 +52,10 @@ def load():
         return _lib
     if not os.path.exists(_LIB):
         build()
+    # one OpenMP thread per physical core unless the caller says otherwise: on the 64-core / 128-thread GPU-box host,
+    # 128 libgomp threads ran the all-cores mode 20-40x SLOWER than 64 (measured, tools/cpu_probe.py)
+    if "OMP_NUM_THREADS" not in os.environ:
+        os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 2) // 2))
     lib = C.CDLL(_LIB)
     lib.orc_scene_create.restype = C.c_void_p
     lib.orc_scene_create.argtypes = [C.POINTER(C.c_float), C.c_int, C.POINTER(C.c_float), C.c_int]

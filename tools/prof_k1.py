@@ -14,6 +14,9 @@ with Context(0) as ctx:
     ctx.set_source(scene)
     ctx.find_planes(T, 0.05, want_planes=False)
     ctx.freeze_planes_f32()
-    for wd in (True, False):
+    for wd in (False, True):
+        for f64 in (False, True):
+            ctx.time_reduce(f64, T, wd, 2, False)          # one-time per-kernel setup outside the timed batch
+    for wd in (False, True):
         print("f32 planes wd", wd, ctx.time_reduce(False, T, wd, reps, False), "ms")
         print("f64 planes wd", wd, ctx.time_reduce(True, T, wd, reps, False), "ms")
