@@ -38,6 +38,7 @@ C2_ITERS = 50
 C4_SLOTS = 10_000_000
 C4_RADIUS = 0.05
 ALG_BYTES_PER_SLOT = 32          # float4 point + float4 plane
+K1_NCU_TRAFFIC_BYTES = 320.06e6 + 3.56e6   # dram read + write of one 10 M-slot K1 launch (ncu, profiles/)
 
 
 def env_int(name, default):
@@ -257,21 +258,19 @@ def run_ours(args, rank, local_rank, world):
     d2h = int(ctypes.sizeof(IterLog) * C2_ITERS + 472)
 
     # ---------------- C4: K1 reduction roofline (sharded at N > 1) ----------------
+    from dcreg_b200.parallel import init_sharded, shard_range
     n_total = C4_SLOTS
     scene = make_corridor(n_total, seed=44, noise=0.002)
-    lo, hi = rank * n_total // world, (rank + 1) * n_total // world
+    lo, hi = shard_range(n_total, rank, world)
     Tc = np.eye(4); Tc[:3, 3] = [0.004, 0.003, -0.002]
     ctx.set_target(scene, C4_RADIUS)
     ctx.set_source(scene[lo:hi])
-    ctx.set_global_source_count(n_total)
     ctx.find_planes(Tc, C4_RADIUS, want_planes=False)     # correspondences once; planes stay on the device
     ctx.freeze_planes_f32()
     if world > 1:
-        idt = torch.zeros(128, dtype=torch.uint8, device=dev)
-        if rank == 0:
-            idt = torch.tensor(list(ctx.comm_unique_id()), dtype=torch.uint8, device=dev)
-        dist.broadcast(idt, 0)
-        ctx.comm_init(bytes(idt.cpu().tolist()), rank, world)
+        init_sharded(ctx, dist, n_total, device=dev)      # NCCL comm inside the C library; id via torch.distributed
+    else:
+        ctx.set_global_source_count(n_total)
     out27, stats = ctx.reduce_device(False, Tc, False)    # warm-up + sanity
     for wd in (False, True):
         for f64 in (False, True):
@@ -314,7 +313,9 @@ def run_ours(args, rank, local_rank, world):
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": int(launches),
             "roofline": {"kernel": "k1s::reduce_stream_kernel<float4, wd=false> (K1)", "bound": "hbm", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": K1_NCU_TRAFFIC_BYTES * n_local / C4_SLOTS, "traffic_source": "ncu --set full dram__bytes_read+write per 10 M-slot launch, profiles/k1_r1_final_ncu_summary.txt",
+                         "peak_source": peak_src,
                          "ms_per_launch": k1_ms, "slots_per_launch": n_local, "bytes_per_slot": ALG_BYTES_PER_SLOT},
             "reduction": {"mpoints_per_s": mpts, "slots_total": n_total, "ms": k1_ms,
                           "weight_derivative_variant_ms": k1_ms_wd,
@@ -322,7 +323,8 @@ def run_ours(args, rank, local_rank, world):
                           "f64_plane_variant_ms": k1_ms_f64,
                           "f64_plane_variant_gbs": 48 * n_local / (k1_ms_f64 * 1e-3) / 1e9,
                           "n_effective": int(stats[1]),
-                          "collective": "ncclAllReduce 32 doubles per launch" if world > 1 else None},
+                          "collective": "ncclAllReduce 32 doubles per launch (inside the timed region)" if world > 1 else None,
+                          "sharding": f"{world} contiguous point blocks of {n_local} slots" if world > 1 else None},
             "cpu_baseline": cpu,
             "clocks": clocks,
         }
