@@ -214,7 +214,7 @@ def run_ours(args, rank, local_rank, world):
     pts_pinned = pinned.numpy()
     T0 = g2_initial_pose()
     prm = c2_params(default_params)
-    ctx.set_target(pts, 1.0)                 # spatial index build: setup, outside the reference's timed region too
+    ctx.set_target(pts, 1.0)                 # cell = radius (measured fastest; finer grids are exact too but slower): index build: setup, outside the reference's timed region too
     ctx.set_source(pts_pinned)
     for _ in range(max(args.warmup, 3)):
         res = ctx.icp_run(prm, T0, want_log=False)

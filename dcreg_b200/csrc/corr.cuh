@@ -30,6 +30,7 @@ struct Grid {
     float4* pts;                // n target points grouped by cell
     int n;
     int dense;                  // 1: dense mode, 0: hash mode
+    int rings;                  // ceil(search radius / cell edge): cells per direction a query must look at
     double inv_cell;            // 1 / cell edge
     // dense mode
     int ox, oy, oz;             // cell coordinates of the bounding box's minimum corner
@@ -270,51 +271,74 @@ __device__ __forceinline__ void knn_scan_range(const float4* __restrict__ pts, i
     }
 }
 
-// distance from coordinate v (inside cell c) to the cell c + dc along one axis: 0 for the own cell
-__device__ __forceinline__ float axis_gap(float v, int c, int dc, float cell) {
-    if (dc == 0) return 0.0f;
-    const float lo = (float)c * cell;
-    return dc < 0 ? (v - lo) : ((lo + cell) - v);
-}
-
 __device__ __forceinline__ void knn_search(const Grid& g, float qx, float qy, float qz, Knn5& k) {
     const int cx = cell_coord(qx, g.inv_cell), cy = cell_coord(qy, g.inv_cell), cz = cell_coord(qz, g.inv_cell);
     if (g.dense) {
-        // Row order: own row first, then the 4 face rows, then the 4 edge rows; inside a row the own cell first.
-        // A cell (or a whole row) is skipped when the box distance to it already exceeds the current 5th-best
-        // distance (strictly, with a 1e-5 relative safety margin for the float arithmetic of the bound), which
-        // keeps the search exact: no skipped cell can hold a point that would enter the result.
-        // The loops are deliberately NOT unrolled: one copy of the scan loop keeps the kernel inside the
-        // instruction cache (the fully unrolled version stalled on instruction fetch, profiles/icp_r3).
+        // K = ceil(radius / cell) rings of cells cover the search radius (K = 1 when cell = radius; a finer grid,
+        // cell = radius / 2, K = 2, scans ~3x fewer candidates because most cells are pruned by their box distance).
+        // Rows (dy, dz) are visited in rings of growing max(|dy|, |dz|); inside a row the own column first, then
+        // outwards.  A row / cell is skipped only when its box distance exceeds the current 5th-best distance
+        // (strictly, with a 1e-5 relative margin for the float arithmetic of the bound), so the search stays exact.
+        // Loops are deliberately NOT unrolled: one copy of the scan loop keeps the kernel inside the instruction
+        // cache (the fully unrolled version stalled on instruction fetch, profiles/icp_iteration_r1).
+        const int K = g.rings;
         const float cell = (float)(1.0 / g.inv_cell);
         const int lx = cx - g.ox, ly = cy - g.oy, lz = cz - g.oz;
-        if (lx + 1 < 0 || lx - 1 >= g.nx) return;
-        const float gx[3] = {axis_gap(qx, cx, -1, cell), 0.0f, axis_gap(qx, cx, +1, cell)};
-        const unsigned long long order = 0x862075314ull;       // rows r = (dz+1)*3 + (dy+1) in visiting order 4,1,3,5,7,0,2,6,8
+        if (lx + K < 0 || lx - K >= g.nx) return;
+        // position inside the own cell, in [0, cell) up to float rounding of cx * cell: every gap below is shrunk
+        // by an absolute eps that covers that rounding, so a bound can only be too small (never prunes a hit)
+        const float eps = 2e-6f * (fabsf(qx) + fabsf(qy) + fabsf(qz) + cell);
+        const float fx = qx - (float)cx * cell, fy = qy - (float)cy * cell, fz = qz - (float)cz * cell;
 #pragma unroll 1
-        for (int o = 0; o < 9; ++o) {
-            const int r = (int)((order >> (4 * o)) & 0xF);
-            const int dy = (r % 3) - 1, dz = (r / 3) - 1;
-            const int yy = ly + dy, zz = lz + dz;
-            if (yy < 0 || yy >= g.ny || zz < 0 || zz >= g.nz) continue;
-            const float gy = axis_gap(qy, cy, dy, cell), gz = axis_gap(qz, cz, dz, cell);
-            const float row_lb = (gy * gy + gz * gz) * 0.99999f;
-            if (row_lb > k.d2[4]) continue;
-            const int* rowp = g.cell_start + (size_t)(zz * g.ny + yy) * g.nx;
-            int cs[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) cs[j] = __ldg(rowp + min(max(lx - 1 + j, 0), g.nx));   // x = nx is the row end
+        for (int ring = 0; ring <= K; ++ring) {
+            // a whole ring is at least (ring - 1) * cell + (distance to the own cell's nearest face) away
+            if (ring > 1) {
+                const float m = fmaxf(fminf(fminf(fy, cell - fy), fminf(fz, cell - fz)) + (float)(ring - 1) * cell - eps, 0.0f);
+                if (m * m * 0.99999f > k.d2[4]) break;
+            }
 #pragma unroll 1
-            for (int c = 0; c < 3; ++c) {
-                const int col = (c == 0) ? 1 : (c == 1 ? 0 : 2);                             // own column first
-                if (col != 1 && (row_lb + gx[col] * gx[col] * 0.99999f) > k.d2[4]) continue;
-                knn_scan_range(g.pts, cs[col], cs[col + 1], qx, qy, qz, k);
+            for (int dz = -ring; dz <= ring; ++dz) {
+                const int zz = lz + dz;
+                if (zz < 0 || zz >= g.nz) continue;
+                const float gz = dz == 0 ? 0.0f : fmaxf((dz < 0 ? fz + (float)(-dz - 1) * cell : (cell - fz) + (float)(dz - 1) * cell) - eps, 0.0f);
+                const int stepy = (dz == -ring || dz == ring) ? 1 : 2 * ring;     // only the ring's boundary rows
+#pragma unroll 1
+                for (int dy = -ring; dy <= ring; dy += (stepy > 0 ? stepy : 1)) {
+                    const int yy = ly + dy;
+                    if (yy < 0 || yy >= g.ny) continue;
+                    const float gy = dy == 0 ? 0.0f : fmaxf((dy < 0 ? fy + (float)(-dy - 1) * cell : (cell - fy) + (float)(dy - 1) * cell) - eps, 0.0f);
+                    const float row_lb = (gy * gy + gz * gz) * 0.99999f;
+                    if (row_lb > k.d2[4]) continue;
+                    const int* rowp = g.cell_start + (size_t)(zz * g.ny + yy) * g.nx;
+                    // own column, then +-1, +-2, ... : stop a side once its gap bound exceeds the 5th-best distance
+                    {
+                        const int x0 = min(max(lx, 0), g.nx), x1 = min(max(lx + 1, 0), g.nx);
+                        knn_scan_range(g.pts, __ldg(rowp + x0), __ldg(rowp + x1), qx, qy, qz, k);
+                    }
+#pragma unroll 1
+                    for (int dx = 1; dx <= K; ++dx) {
+                        const float gl = fmaxf(fx + (float)(dx - 1) * cell - eps, 0.0f);
+                        const float gr = fmaxf((cell - fx) + (float)(dx - 1) * cell - eps, 0.0f);
+                        const bool left = (row_lb + gl * gl * 0.99999f) <= k.d2[4];
+                        if (left) {
+                            const int x0 = min(max(lx - dx, 0), g.nx), x1 = min(max(lx - dx + 1, 0), g.nx);
+                            knn_scan_range(g.pts, __ldg(rowp + x0), __ldg(rowp + x1), qx, qy, qz, k);
+                        }
+                        const bool right = (row_lb + gr * gr * 0.99999f) <= k.d2[4];
+                        if (right) {
+                            const int x0 = min(max(lx + dx, 0), g.nx), x1 = min(max(lx + dx + 1, 0), g.nx);
+                            knn_scan_range(g.pts, __ldg(rowp + x0), __ldg(rowp + x1), qx, qy, qz, k);
+                        }
+                        if (!left && !right) break;
+                    }
+                }
             }
         }
     } else {
-        for (int dz = -1; dz <= 1; ++dz)
-            for (int dy = -1; dy <= 1; ++dy)
-                for (int dx = -1; dx <= 1; ++dx) {
+        const int K = g.rings;
+        for (int dz = -K; dz <= K; ++dz)
+            for (int dy = -K; dy <= K; ++dy)
+                for (int dx = -K; dx <= K; ++dx) {
                     const unsigned long long key = pack_key(cx + dx, cy + dy, cz + dz);
                     unsigned int slot = hash_key(key) & g.mask;
                     int start = 0, cnt = 0;

@@ -119,10 +119,15 @@ __global__ void __launch_bounds__(kBlock, 3) icp_iteration_kernel(const __grid_c
 }
 
 // K2 as its own kernel (seam 3, and the sharded loop after the all-reduce).
-__global__ void k2_step_kernel(const double* acc, IcpState* st, dcreg_icp_params prm, dcreg_iter_log* log,
-                               int log_cap) {
-    if (threadIdx.x != 0 || st->done) return;
-    k2::icp_step(acc, st, prm, log, log_cap);
+__global__ void __launch_bounds__(32) k2_step_kernel(const double* acc, IcpState* st, dcreg_icp_params prm,
+                                                     dcreg_iter_log* log, int log_cap) {
+    __shared__ k2::WarpSmem sm;
+    if (st->done) return;
+    if (prm.detection == DCREG_DET_SCHUR_CONDITION_NUMBER && prm.handling == DCREG_HAND_PRECONDITIONED_CG) {
+        k2::icp_step_warp_ours(acc, st, prm, log, log_cap, sm);       // all 32 lanes cooperate
+    } else if (threadIdx.x == 0) {
+        k2::icp_step(acc, st, prm, log, log_cap);                     // baseline methods: generic single-thread path
+    }
 }
 
 __global__ void k2_analyze_kernel(const double* v27, dcreg_icp_params prm, dcreg_analysis* out, double* dx) {
@@ -671,6 +676,14 @@ static int launch_iteration(dcreg_ctx* ctx, const dcreg_icp_params* prm, const f
     a.src = src; a.n = ctx->n_src; a.grid = ctx->grid; a.state = ctx->d_state;
     a.partials = ctx->d_partials; a.counter = ctx->d_counter; a.acc = ctx->d_acc;
     a.planes_out = planes_out; a.prm = *prm;
+    {   // rings of cells that cover the search radius (exactness of the 5-NN-within-radius rule)
+        const int rings = (int)ceil(prm->search_radius / ctx->cell_size - 1e-9);
+        if (rings < 1 || rings > 4) {
+            ctx->err = "search_radius / target cell_size must be in (0, 4]: rebuild the target index with a larger cell";
+            return DCREG_BAD_ARG;
+        }
+        a.grid.rings = rings;
+    }
     if (prm->use_weight_derivative) icp_iteration_kernel<true><<<grid, kBlock, 0, ctx->stream>>>(a);
     else icp_iteration_kernel<false><<<grid, kBlock, 0, ctx->stream>>>(a);
     ctx->launches++;

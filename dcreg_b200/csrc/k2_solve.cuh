@@ -419,4 +419,199 @@ __device__ inline void icp_step(const double* acc, IcpState* st, const dcreg_icp
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Warp-cooperative K2 step for the "Ours" method (SCHUR_CONDITION_NUMBER + PRECONDITIONED_CG), the per-iteration
+// critical path of the loop.  Why: executed by a single thread the step is ~7 k dependent FP64 instructions; on B200 a
+// dependent DFMA issues every ~40 cycles and the straight-line code is fetched cold on every launch (profiles/
+// k2_step_r1: 101 k cycles, top stall = no_instruction).  Here the 32 lanes share the work: the two 3x3 inverses and
+// the two 3x3 Jacobi EVDs run on lanes 0/1 side by side, Schur products and the preconditioner are one entry per
+// lane, and the PCG mat-vecs are row-per-lane with shuffle broadcasts and butterfly dot products.  The in-loop record
+// gets the non-analysis fields; the analysis block is (re)computed for every record by log_fill_kernel after the run
+// with the same single-thread code the host seam uses, so mask / P / PCG counts in the log stay oracle-identical.
+// ------------------------------------------------------------------------------------------------------------------
+struct WarpSmem {
+    double H[36], g[6];
+    double inv[2][9];        // [0] = H_tt^-1, [1] = H_RR^-1
+    double S[2][9];          // [0] = S_R, [1] = S_t
+    double lam[2][3], V[2][9];
+    double P[36];
+    double dx[6];
+    int ok[2];
+};
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    return v;
+}
+__device__ __forceinline__ double row_dot_bcast(const double (&row)[6], double v) {   // sum_j row[j] * v(lane j)
+    double s = 0.0;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) s = fma(row[j], __shfl_sync(0xffffffffu, v, j), s);
+    return s;
+}
+
+// PCG on H x = g (paper Alg. 3): lanes 0..5 own rows/components, all 32 lanes execute.  Returns iterations used.
+__device__ __forceinline__ int pcg6_warp(const WarpSmem& sm, int lane, int max_iter, double tol, double& x_out) {
+    double Hrow[6], Prow[6];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) { Hrow[j] = lane < 6 ? sm.H[lane * 6 + j] : 0.0; Prow[j] = lane < 6 ? sm.P[lane * 6 + j] : 0.0; }
+    double x = 0.0, r = lane < 6 ? sm.g[lane] : 0.0;
+    double z = row_dot_bcast(Prow, r);
+    double p = z;
+    double rz = warp_sum(r * z);
+    int it;
+    for (it = 1; it <= max_iter; ++it) {
+        const double Hp = row_dot_bcast(Hrow, p);
+        const double alpha = rz / warp_sum(p * Hp);
+        x = fma(alpha, p, x);
+        r = fma(-alpha, Hp, r);
+        const double rn = sqrt(warp_sum(r * r));
+        if (rn < tol) break;                                 // identical in every lane: uniform branch
+        z = row_dot_bcast(Prow, r);
+        const double rz_new = warp_sum(r * z);
+        p = fma(rz_new / rz, p, z);
+        rz = rz_new;
+    }
+    x_out = x;
+    return it > max_iter ? max_iter : it;
+}
+
+// One K2 step by one warp.  Same observable behaviour as icp_step for the "Ours" method.
+__device__ inline void icp_step_warp_ours(const double* acc, IcpState* st, const dcreg_icp_params& prm,
+                                          dcreg_iter_log* log, int log_cap, WarpSmem& sm) {
+    const int lane = threadIdx.x & 31;
+    const int iter = st->iter;
+    dcreg_iter_log* rec = (log != nullptr && iter < log_cap) ? &log[iter] : nullptr;
+    const int n_eff = (int)(acc[kAccNeff] + 0.5);
+    const int n_pt = (int)(acc[kAccNpt] + 0.5);
+    for (int e = lane; e < 36; e += 32) {
+        const int i = e / 6, j = e % 6, a = i < j ? i : j, b = i < j ? j : i;
+        sm.H[e] = acc[a * 6 - (a * (a - 1)) / 2 + (b - a)];
+    }
+    if (lane < 6) sm.g[lane] = acc[21 + lane];
+    if (rec) {
+        if (lane < 27) rec->H27[lane] = acc[lane];
+        if (lane == 0) { rec->iter = iter; rec->n_effective = n_eff; rec->n_corr_pt = n_pt; rec->status = DCREG_OK; }
+    }
+    __syncwarp();
+    if (n_eff < prm.min_effective_points) {                 // icp_test_runner.cpp:1847-1854 (uniform branch)
+        if (lane == 0) {
+            st->iter = iter + 1; st->done = 1; st->converged = 0; st->status = DCREG_NOT_ENOUGH_POINTS;
+            if (rec) {
+                rec->status = DCREG_NOT_ENOUGH_POINTS; rec->rmse = 0.0; rec->fitness = 0.0; rec->objective = 0.0;
+                for (int i = 0; i < 6; ++i) { rec->gradient[i] = 0.0; rec->dx[i] = 0.0; }
+                for (int r = 0; r < 3; ++r) {
+                    for (int c = 0; c < 3; ++c) rec->T[r * 4 + c] = st->R[r * 3 + c];
+                    rec->T[r * 4 + 3] = st->t[r];
+                }
+                rec->T[12] = rec->T[13] = rec->T[14] = 0.0; rec->T[15] = 1.0;
+            }
+        }
+        return;
+    }
+    // ---- block inverses (FullPivLU semantics), lanes 0 / 1 ----
+    if (lane < 2) {
+        double M[9];
+        const int o = lane == 0 ? 3 : 0;                     // lane 0: H_tt, lane 1: H_RR
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) M[i * 3 + j] = sm.H[(i + o) * 6 + j + o];
+        sm.ok[lane] = dla::fullpiv_inverse<3>(M, sm.inv[lane]) ? 1 : 0;
+    }
+    __syncwarp();
+    const bool schur_ok = sm.ok[0] && sm.ok[1];
+    int degenerate = 0;
+    if (schur_ok) {
+        // ---- Schur complements (icp_test_runner.cpp:2443-2447, paper Eq. 18): one entry per lane ----
+        double sval = 0.0;
+        if (lane < 18) {
+            const int blk = lane / 9, e = lane % 9, i = e / 3, j = e % 3;
+            // blk 0: S_R = H_RR - (H_Rt Htt^-1) H_tR ; blk 1: S_t = H_tt - (H_tR HRR^-1) H_Rt
+            const int ro = blk == 0 ? 0 : 3, co = blk == 0 ? 3 : 0;
+            const double* Inv = sm.inv[blk];
+            double t2 = 0.0;
+#pragma unroll
+            for (int m = 0; m < 3; ++m) {
+                double t1 = 0.0;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) t1 += sm.H[(ro + i) * 6 + co + k] * Inv[k * 3 + m];
+                t2 += t1 * sm.H[(co + m) * 6 + ro + j];
+            }
+            sval = sm.H[(ro + i) * 6 + ro + j] - t2;
+            sm.S[blk][e] = sval;
+        }
+        __syncwarp();
+        if (lane < 18) {
+            const int blk = lane / 9, e = lane % 9, i = e / 3, j = e % 3;
+            sval = 0.5 * (sval + sm.S[blk][j * 3 + i]);
+        }
+        __syncwarp();
+        if (lane < 18) sm.S[lane / 9][lane % 9] = sval;
+        __syncwarp();
+        if (lane < 2) dla::jacobi_eigh3(sm.S[lane], sm.lam[lane], sm.V[lane]);
+        __syncwarp();
+        // ---- detection (Eq. 20-21) and preconditioner (Eq. 43-46) ----
+        bool deg = false;
+        if (lane < 6) {
+            const double* l = sm.lam[lane / 3];
+            deg = l[2] / fmax(l[lane % 3], 1e-12) > prm.cond_thresh;
+        }
+        degenerate = __ballot_sync(0xffffffffu, deg) != 0u;
+        for (int e = lane; e < 36; e += 32) {
+            const int i = e / 6, j = e % 6;
+            double v = 0.0;
+            if (i / 3 == j / 3) {
+                const int blk = i / 3;
+                const double* l = sm.lam[blk];
+                const double* Vb = sm.V[blk];
+                for (int k = 0; k < 3; ++k) v += Vb[(i % 3) * 3 + k] * Vb[(j % 3) * 3 + k] / fmax(l[k], l[2] / prm.kappa_target);
+            }
+            sm.P[e] = v;
+        }
+        __syncwarp();
+    }
+    // ---- solve ----
+    if (degenerate) {
+        double xi;
+        pcg6_warp(sm, lane, prm.pcg_max_iter, prm.pcg_tol, xi);
+        if (lane < 6) sm.dx[lane] = xi;
+    } else if (lane == 0) {
+        qr6(sm.H, sm.g, sm.dx);                              // dcreg.hpp:190
+    }
+    __syncwarp();
+    const double dxi = lane < 6 ? sm.dx[lane] : 0.0;
+    const bool finite = __ballot_sync(0xffffffffu, !isfinite(dxi)) == 0u;
+    const double fitness = st->n_source_total > 0 ? (double)n_pt / (double)st->n_source_total : 0.0;
+    const double rmse = sqrt(acc[kAccSumR2] / (double)n_eff);
+    if (rec) {
+        if (lane == 0) { rec->rmse = rmse; rec->fitness = fitness; rec->objective = 0.5 * acc[kAccSumB2]; }
+        if (lane < 6) rec->gradient[lane] = -acc[21 + lane];
+    }
+    if (!finite) {                                          // icp_test_runner.cpp:1942-1950
+        if (lane == 0) { st->done = 1; st->converged = 0; st->status = DCREG_NONFINITE_UPDATE; }
+        if (rec) { if (lane == 0) rec->status = DCREG_NONFINITE_UPDATE; if (lane < 6) rec->dx[lane] = 0.0; }
+        return;
+    }
+    for (int e = lane; e < 36; e += 32) st->H_last[e] = sm.H[e];     // matAtA_last, icp_test_runner.cpp:1965
+    if (lane == 0) {
+        boxplus(st->R, st->t, sm.dx);                        // icp_test_runner.cpp:1953
+        const double dR = sqrt(sm.dx[0] * sm.dx[0] + sm.dx[1] * sm.dx[1] + sm.dx[2] * sm.dx[2]);
+        const double dT = sqrt(sm.dx[3] * sm.dx[3] + sm.dx[4] * sm.dx[4] + sm.dx[5] * sm.dx[5]);
+        st->iter = iter + 1;
+        if (!prm.fixed_iterations && dR < prm.conv_thresh_rot && dT < prm.conv_thresh_trans) {
+            st->converged = 1; st->done = 1;                 // icp_test_runner.cpp:1998-2002
+        } else if (st->iter >= prm.max_iterations) {
+            st->done = 1;
+        }
+    }
+    __syncwarp();
+    if (rec) {
+        if (lane < 6) rec->dx[lane] = sm.dx[lane];
+        if (lane < 16) {
+            const int r = lane / 4, c = lane % 4;
+            rec->T[lane] = r == 3 ? (c == 3 ? 1.0 : 0.0) : (c == 3 ? st->t[r] : st->R[r * 3 + c]);
+        }
+    }
+}
+
 }  // namespace k2

@@ -246,6 +246,20 @@ def test_find_planes_matches_oracle(ctx, golden, cylinder, tree, setup):
     assert np.abs(planes - ref).max() < 1e-9
 
 
+@pytest.mark.parametrize("div", [1, 2, 3, 4])
+def test_find_planes_finer_grids_are_exact(ctx, golden, cylinder, tree, div):
+    """cell = radius / div (div rings of cells per direction): same accept set and planes as the kd-tree."""
+    T = init_T(golden["G2"]["setup"])
+    ctx.set_source(cylinder)
+    ctx.set_target(cylinder, 1.0 / div)
+    planes, npt = ctx.find_planes(T, 1.0)
+    corr = o.find_correspondences(cylinder, cylinder, tree, T[:3, :3], T[:3, 3], 1.0, False)
+    assert npt == corr.n_pt
+    ref = np.concatenate([corr.n, corr.d[:, None]], axis=1); ref[~corr.has_plane] = 0
+    assert np.array_equal(np.abs(ref[:, :3]).sum(1) > 0, np.abs(planes[:, :3]).sum(1) > 0)
+    assert np.abs(planes - ref).max() < 1e-9
+
+
 def test_find_planes_random_cloud_radius_half(ctx):
     rng = np.random.default_rng(3)
     tgt = rng.uniform(-5, 5, (60_000, 3)).astype(np.float32)
@@ -351,6 +365,51 @@ def test_icp_corridor_weakest_translation_is_the_axis(ctx):
     v = res.logs[0].analysis.np("schur_V_trans").reshape(3, 3)[:, 0]
     assert abs(v[0]) > 0.99                                        # weakest translation direction = corridor axis x
     assert res.logs[0].analysis.is_degenerate == int(logs[0].analysis.is_degenerate)
+
+
+def test_icp_parking_lot_standin_c3(ctx):
+    """BASELINE config C3 (icp_pk01.yaml shapes; the real pair is not shipped): ~6 k-point scan vs a 0.5 M-point
+    ground-dominated map, radius 0.5, 30 iterations, ROT 1e-5 / TRANS 1e-3, init offset of icp_pk01.yaml:30-44.
+    Degeneracy eigenvalues, masks and the pose against the C oracle."""
+    import dcreg_oracle_c as oc
+    from dcreg_b200.scenes import make_parking
+    scan, tgt = make_parking(n_map=500_000, n_scan=6_000, seed=43)
+    T0 = o.pose6d_to_matrix(0.15, 0.12, 0.13, math.radians(0.015), math.radians(1.31), math.radians(2.17))
+    prm = o.Params(search_radius=0.5, max_iterations=30, conv_rot=1e-5, conv_trans=1e-3, kappa_target=10.0)
+    sc = oc.Scene(scan, tgt)
+    cp = oc.make_params(search_radius=0.5, max_iterations=30, conv_rot=1e-5, conv_trans=1e-3, kappa_target=10.0)
+    st, conv, n_it, Tc, clogs = sc.icp_run(cp, T0)
+    sc.close()
+    ctx.set_source(scan); ctx.set_target(tgt, 0.5)
+    res = ctx.icp_run(gpu_params(prm), T0)
+    assert res.status == st and res.converged == conv and res.iterations == n_it
+    for C, G in zip(clogs, res.logs):
+        assert G.n_effective == C.n_eff and G.n_corr_pt == C.n_pt
+        assert list(G.analysis.degenerate_mask) == list(C.mask)
+        assert np.allclose(G.analysis.np("lambda_schur_rot"), C.lam_schur_rot, rtol=1e-8)
+        assert np.allclose(G.analysis.np("lambda_schur_trans"), C.lam_schur_trans, rtol=1e-8)
+        assert np.abs(np.array(G.dx) - np.array(C.dx)).max() < 1e-8
+    assert o.se3_log_distance(Tc, res.T) < 1e-6
+    assert any(G.analysis.is_degenerate for G in res.logs)          # planar scene: x / y / yaw weakly constrained
+
+
+def test_icp_monte_carlo_trials_c5(ctx, cylinder):
+    """BASELINE config C5 at test size: seeded perturbations of the cylinder pair (t ~ U[-1,1]^3 m, rpy ~ U[-3,3]^3 deg,
+    seed 45), one independent run per trial (replicas; no collective), every final pose against the C oracle."""
+    import dcreg_oracle_c as oc
+    rng = np.random.default_rng(45)
+    sc = oc.Scene(cylinder, cylinder)
+    ctx.set_source(cylinder); ctx.set_target(cylinder, 1.0)
+    prm = o.Params(kappa_target=10.0, conv_rot=1e-5, conv_trans=1e-3)
+    cp = oc.make_params(kappa_target=10.0, conv_rot=1e-5, conv_trans=1e-3)
+    for trial in range(12):
+        t = rng.uniform(-1, 1, 3); rpy = np.radians(rng.uniform(-3, 3, 3))
+        T0 = o.pose6d_to_matrix(t[0], t[1], t[2], rpy[0], rpy[1], rpy[2])
+        st, conv, n_it, Tc, clogs = sc.icp_run(cp, T0)
+        res = ctx.icp_run(gpu_params(prm), T0, want_log=False)
+        assert res.status == st and res.converged == conv and res.iterations == n_it, trial
+        assert o.se3_log_distance(Tc, res.T) < 1e-6, trial
+    sc.close()
 
 
 def test_icp_abort_not_enough_points(ctx, cylinder):

@@ -9,7 +9,7 @@ n = int(os.environ.get("ICP_POINTS", 100_000))
 iters = int(os.environ.get("ICP_ITERS", 6))
 pts = make_cylinder(n, seed=42)
 with Context(0) as ctx:
-    ctx.set_target(pts, 1.0)
+    ctx.set_target(pts, float(os.environ.get("ICP_CELL", "1.0")))
     ctx.set_source(pts)
     prm = default_params(max_iterations=iters, fixed_iterations=1, kappa_target=10.0, use_weight_derivative=int(os.environ.get("ICP_WD", "0")))
     for _ in range(2):
