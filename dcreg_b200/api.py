@@ -86,7 +86,7 @@ EXPORTS = [
     "dcreg_stream", "dcreg_set_source", "dcreg_set_target", "dcreg_find_planes",
     "dcreg_reduce_normal_equations", "dcreg_reduce_normal_equations_f64plane",
     "dcreg_reduce_normal_equations_host", "dcreg_analyze_and_solve", "dcreg_solve_pcg", "dcreg_icp_run",
-    "dcreg_icp_run_host_planes", "dcreg_last_covariance", "dcreg_comm_unique_id", "dcreg_comm_init",
+    "dcreg_icp_run_host_planes", "dcreg_last_covariance", "dcreg_point_to_point_metrics", "dcreg_comm_unique_id", "dcreg_comm_init",
     "dcreg_comm_destroy", "dcreg_set_global_source_count", "dcreg_launch_count", "dcreg_device_source",
     "dcreg_device_planes_f64", "dcreg_device_planes_f32", "dcreg_freeze_planes_f32", "dcreg_time_reduce",
 ]
@@ -122,6 +122,7 @@ def load_library():
     lib.dcreg_icp_run_host_planes.argtypes = [vp, C.POINTER(IcpParams), dp, PLANE_CALLBACK, vp, dp,
                                               C.POINTER(IterLog), ci, C.POINTER(ci), C.POINTER(ci)]
     lib.dcreg_last_covariance.argtypes = [vp, dp]
+    lib.dcreg_point_to_point_metrics.argtypes = [vp, dp, C.c_double, dp]
     lib.dcreg_comm_unique_id.argtypes = [vp, C.POINTER(C.c_uint8)]
     lib.dcreg_comm_init.argtypes = [vp, C.POINTER(C.c_uint8), ci, ci]
     lib.dcreg_comm_destroy.argtypes = [vp]
@@ -345,6 +346,13 @@ class Context:
         cov = np.empty((6, 6))
         self._check(self.lib.dcreg_last_covariance(self._h, _dptr(cov)))
         return cov
+
+    def point_to_point_metrics(self, T, error_threshold: float):
+        """calculatePointToPointError on the device: returns dict(rmse, fitness, chamfer, n_valid)."""
+        T = np.ascontiguousarray(T, dtype=np.float64)
+        out = np.empty(4)
+        self._check(self.lib.dcreg_point_to_point_metrics(self._h, _dptr(T), float(error_threshold), _dptr(out)))
+        return {"rmse": out[0], "fitness": out[1], "chamfer": out[2], "n_valid": int(out[3])}
 
     # -- multi-GPU --
     def comm_unique_id(self) -> bytes:

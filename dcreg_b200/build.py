@@ -54,5 +54,28 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB_PATH
 
 
+HOST_DIR = os.path.join(PKG_DIR, "host")
+RUNNER_PATH = os.path.join(PKG_DIR, "icp_test_runner")
+RUNNER_SOURCES = ["icp_test_runner.cpp"]
+RUNNER_HEADERS = ["yaml_lite.hpp", "pcd_io.hpp", "../../include/dcreg_b200.h"]
+
+
+def build_runner(force: bool = False) -> str:
+    """g++ build of the host CLI (the reference's `icp_test_runner` executable) against the C ABI library."""
+    build(force=False)
+    deps = [os.path.join(HOST_DIR, f) for f in RUNNER_SOURCES + RUNNER_HEADERS] + [LIB_PATH]
+    if not force and os.path.exists(RUNNER_PATH) and all(os.path.getmtime(d) <= os.path.getmtime(RUNNER_PATH) for d in deps):
+        return RUNNER_PATH
+    cxx = os.environ.get("CXX") or shutil.which("g++") or "g++"
+    cmd = [cxx, "-O2", "-std=c++17", "-Wall", "-Wextra"] + [os.path.join(HOST_DIR, s) for s in RUNNER_SOURCES] + [
+        "-o", RUNNER_PATH, "-L" + PKG_DIR, "-ldcreg_b200", "-Wl,-rpath,$ORIGIN"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError("g++ failed building icp_test_runner")
+    return RUNNER_PATH
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose=True))
+    print(build_runner(force="--force" in sys.argv))

@@ -353,6 +353,99 @@ __device__ __forceinline__ void knn_search(const Grid& g, float qx, float qy, fl
     }
 }
 
+// ---- exact 1-NN (post-run point-to-point metrics, DCReg/include/utils.hpp:538-589) ---------------------------
+// Nearest target point of q in a dense grid: rings of cells of growing Chebyshev radius around q's cell, clipped to
+// the grid box, until the best distance found is no larger than the distance to the next ring.  FLANN-style float32
+// squared distances.  Returns the squared distance (3e38 if the grid is empty).
+__device__ __forceinline__ float nn1_search(const Grid& g, float qx, float qy, float qz) {
+    const float cell = (float)(1.0 / g.inv_cell);
+    const int lx = cell_coord(qx, g.inv_cell) - g.ox, ly = cell_coord(qy, g.inv_cell) - g.oy, lz = cell_coord(qz, g.inv_cell) - g.oz;
+    // first ring that can touch the box, last ring that still does
+    const int ox = lx < 0 ? -lx : (lx >= g.nx ? lx - g.nx + 1 : 0);
+    const int oy = ly < 0 ? -ly : (ly >= g.ny ? ly - g.ny + 1 : 0);
+    const int oz = lz < 0 ? -lz : (lz >= g.nz ? lz - g.nz + 1 : 0);
+    const int r0 = max(ox, max(oy, oz));
+    const int r1 = max(max(lx, g.nx - 1 - lx), max(max(ly, g.ny - 1 - ly), max(lz, g.nz - 1 - lz)));
+    float best = 3.0e38f;
+#pragma unroll 1
+    for (int r = r0; r <= r1; ++r) {
+        if (r > 0) {
+            const float lb = (float)(r - 1) * cell * 0.99999f;      // every point of ring r is at least this far
+            if (lb * lb > best) break;
+        }
+        const int z0 = max(-r, -lz), z1 = min(r, g.nz - 1 - lz);
+        const int y0 = max(-r, -ly), y1 = min(r, g.ny - 1 - ly);
+#pragma unroll 1
+        for (int dz = z0; dz <= z1; ++dz) {
+#pragma unroll 1
+            for (int dy = y0; dy <= y1; ++dy) {
+                const int* rowp = g.cell_start + (size_t)((lz + dz) * g.ny + (ly + dy)) * g.nx;
+                const bool shell = (dz == -r) || (dz == r) || (dy == -r) || (dy == r);
+                if (shell) {                                         // whole x-span of the ring, one contiguous range
+                    const int xa = max(lx - r, 0), xb = min(lx + r, g.nx - 1);
+                    if (xa > xb) continue;
+                    const int s = __ldg(rowp + xa), e = __ldg(rowp + xb + 1);
+                    for (int j = s; j < e; ++j) best = fminf(best, dist2(qx, qy, qz, __ldg(&g.pts[j])));
+                } else {                                             // interior row: only the two end cells dx = +-r
+                    for (int sgn = -1; sgn <= 1; sgn += 2) {
+                        const int xx = lx + sgn * r;
+                        if (xx < 0 || xx >= g.nx) continue;
+                        const int s = __ldg(rowp + xx), e = __ldg(rowp + xx + 1);
+                        for (int j = s; j < e; ++j) best = fminf(best, dist2(qx, qy, qz, __ldg(&g.pts[j])));
+                    }
+                }
+            }
+        }
+    }
+    return best;
+}
+
+// per-block partial sums: [0] sum of distances, [1] sum of squared distances below the threshold, [2] count below it.
+// When T != nullptr the query is fl32(T p) (pcl::transformPointCloud: FP64 math, float32 store), else p itself.
+__global__ void nn1_metrics_kernel(const float4* __restrict__ q, long long n, const double* __restrict__ T, Grid g,
+                                   double threshold, double* __restrict__ partials) {
+    __shared__ double sh[3][8];
+    double sd = 0.0, ssq = 0.0, cnt = 0.0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float4 p = __ldg(&q[i]);
+        float x = p.x, y = p.y, z = p.z;
+        if (T) {
+            const double px = p.x, py = p.y, pz = p.z;
+            x = (float)(T[0] * px + T[1] * py + T[2] * pz + T[3]);
+            y = (float)(T[4] * px + T[5] * py + T[6] * pz + T[7]);
+            z = (float)(T[8] * px + T[9] * py + T[10] * pz + T[11]);
+        }
+        const float d2 = nn1_search(g, x, y, z);
+        const double dist = sqrt((double)d2);
+        sd += dist;
+        if (dist < threshold) { ssq += (double)d2; cnt += 1.0; }
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+        sd += __shfl_down_sync(0xffffffffu, sd, off);
+        ssq += __shfl_down_sync(0xffffffffu, ssq, off);
+        cnt += __shfl_down_sync(0xffffffffu, cnt, off);
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) { sh[0][warp] = sd; sh[1][warp] = ssq; sh[2][warp] = cnt; }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        double s = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += sh[threadIdx.x][w];
+        partials[blockIdx.x * 3 + threadIdx.x] = s;
+    }
+}
+
+// transform + float32 store of a cloud (aligned copy for the backward Chamfer pass)
+__global__ void transform_points_kernel(const float4* __restrict__ in, long long n, const double* __restrict__ T,
+                                        float4* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 p = in[i];
+    const double px = p.x, py = p.y, pz = p.z;
+    out[i] = make_float4((float)(T[0] * px + T[1] * py + T[2] * pz + T[3]), (float)(T[4] * px + T[5] * py + T[6] * pz + T[7]),
+                         (float)(T[8] * px + T[9] * py + T[10] * pz + T[11]), p.w);
+}
+
 // Plane through the 5 neighbours: least squares of [nb] x = -1, n = x/|x|, d = 1/|x|, gates
 // |x| >= min_norm and max_j (n.nb_j + d)^2 < thickness^2 (icp_test_runner.cpp:1727-1773).
 // Returns true and (n, d) when a valid plane exists.

@@ -547,55 +547,51 @@ static int device_exclusive_scan(dcreg_ctx* ctx, const int* in, long long n, int
     return DCREG_OK;
 }
 
-int dcreg_set_target(dcreg_ctx* ctx, const float* xyz, int64_t m, int stride, double cell_size) {
-    if (!ctx) return DCREG_BAD_ARG;
-    if (!xyz || m <= 0 || stride < 3 || !(cell_size > 0.0) || m > 0x7fffffffLL) {
-        ctx->err = "dcreg_set_target: empty cloud, stride < 3, cell_size <= 0 or too many points";
-        return DCREG_BAD_ARG;
-    }
-    CK(cudaSetDevice(ctx->device));
-    void* old[] = {ctx->d_tgt, ctx->grid.keys, ctx->grid.cell_start, ctx->grid.hstart, ctx->grid.hcount, ctx->grid.pts};
-    for (void* p : old)
+static void free_grid(corr::Grid* g) {
+    void* ptrs[] = {g->keys, g->cell_start, g->hstart, g->hcount, g->pts};
+    for (void* p : ptrs)
         if (p) cudaFree(p);
-    ctx->d_tgt = nullptr; ctx->grid = corr::Grid{}; ctx->has_grid = false;
-    CK(cudaMalloc(&ctx->d_tgt, (size_t)m * sizeof(float4)));
-    ctx->n_tgt = m;
-    int rc = upload_points(ctx, xyz, m, stride, ctx->d_tgt);
-    if (rc) return rc;
-    corr::Grid& g = ctx->grid;
-    g.n = (int)m; g.inv_cell = 1.0 / cell_size;
-    ctx->cell_size = cell_size;
+    *g = corr::Grid{};
+}
+
+// Group `m` device points by uniform-grid cell (dense when the bounding box has <= kMaxDenseCells cells, hash table
+// otherwise).  Replaces the kd-tree build of ICPContext::setTargetCloud (utils.hpp:393-424).  Synchronises the stream.
+static int build_grid(dcreg_ctx* ctx, const float4* d_pts, long long m, double cell_size, corr::Grid* gout,
+                      long long* ncells_out) {
+    corr::Grid g{};
+    g.n = (int)m; g.inv_cell = 1.0 / cell_size; g.rings = 1;
     CK(cudaMalloc(&g.pts, (size_t)m * sizeof(float4)));
-    // bounding box in cell coordinates
     int hb[6] = {1 << 30, 1 << 30, 1 << 30, -(1 << 30), -(1 << 30), -(1 << 30)};
     int* d_bounds = (int*)(ctx->d_small + 512);
     CK(cudaMemcpyAsync(d_bounds, hb, sizeof(hb), cudaMemcpyHostToDevice, ctx->stream));
-    corr::grid_bounds_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(ctx->d_tgt, (int)m, g.inv_cell, d_bounds);
+    corr::grid_bounds_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(d_pts, (int)m, g.inv_cell, d_bounds);
     ctx->launches++;
     CK(cudaMemcpyAsync(hb, d_bounds, sizeof(hb), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    if (hb[0] < -(1 << 19) || hb[3] > (1 << 19) || hb[1] < -(1 << 19) || hb[4] > (1 << 19) || hb[2] < -(1 << 19) ||
-        hb[5] > (1 << 19)) {
-        ctx->err = "dcreg_set_target: coordinates / cell_size exceed the +-2^19 cell range (NaN or huge coordinates?)";
-        return DCREG_BAD_ARG;
-    }
+    for (int k = 0; k < 3; ++k)
+        if (hb[k] < -(1 << 19) || hb[3 + k] > (1 << 19)) {
+            cudaFree(g.pts);
+            ctx->err = "grid build: coordinates / cell_size exceed the +-2^19 cell range (NaN or huge coordinates?)";
+            return DCREG_BAD_ARG;
+        }
     const long long nx = (long long)hb[3] - hb[0] + 1, ny = (long long)hb[4] - hb[1] + 1, nz = (long long)hb[5] - hb[2] + 1;
     const long long ncells = nx * ny * nz;
     const unsigned nb = (unsigned)((m + 255) / 256);
     int *pt_cell = nullptr, *fill = nullptr, *counts = nullptr;
     CK(cudaMalloc(&pt_cell, (size_t)m * sizeof(int)));
     cudaError_t e = cudaSuccess;
+    int rc = DCREG_OK;
     if (ncells <= corr::kMaxDenseCells) {
         g.dense = 1; g.ox = hb[0]; g.oy = hb[1]; g.oz = hb[2]; g.nx = (int)nx; g.ny = (int)ny; g.nz = (int)nz;
-        ctx->grid_cells = ncells;
+        if (ncells_out) *ncells_out = ncells;
         CK(cudaMalloc(&g.cell_start, (size_t)(ncells + 1) * sizeof(int)));
         CK(cudaMalloc(&counts, (size_t)(ncells + 1) * sizeof(int)));
         CK(cudaMalloc(&fill, (size_t)ncells * sizeof(int)));
         CK(cudaMemsetAsync(counts, 0, (size_t)(ncells + 1) * sizeof(int), ctx->stream));
         CK(cudaMemsetAsync(fill, 0, (size_t)ncells * sizeof(int), ctx->stream));
-        corr::grid_count_dense_kernel<<<nb, 256, 0, ctx->stream>>>(ctx->d_tgt, (int)m, g, pt_cell, counts);
-        if ((rc = device_exclusive_scan(ctx, counts, ncells + 1, g.cell_start))) return rc;
-        corr::grid_scatter_kernel<<<nb, 256, 0, ctx->stream>>>(ctx->d_tgt, (int)m, pt_cell, g.cell_start, fill, g.pts, 0);
+        corr::grid_count_dense_kernel<<<nb, 256, 0, ctx->stream>>>(d_pts, (int)m, g, pt_cell, counts);
+        rc = device_exclusive_scan(ctx, counts, ncells + 1, g.cell_start);
+        corr::grid_scatter_kernel<<<nb, 256, 0, ctx->stream>>>(d_pts, (int)m, pt_cell, g.cell_start, fill, g.pts, 0);
         corr::grid_sort_cells_kernel<<<(unsigned)((ncells + 255) / 256), 256, 0, ctx->stream>>>(g.pts, g.cell_start, nullptr,
                                                                                                g.cell_start + 1, ncells);
         ctx->launches += 3;
@@ -604,7 +600,7 @@ int dcreg_set_target(dcreg_ctx* ctx, const float* xyz, int64_t m, int stride, do
         unsigned int cap = 1024;
         while ((long long)cap < 2 * m) cap <<= 1;
         g.dense = 0; g.mask = cap - 1;
-        ctx->grid_cells = 0;
+        if (ncells_out) *ncells_out = 0;
         CK(cudaMalloc(&g.keys, (size_t)cap * sizeof(unsigned long long)));
         CK(cudaMalloc(&g.hstart, (size_t)cap * sizeof(int)));
         CK(cudaMalloc(&g.hcount, (size_t)cap * sizeof(int)));
@@ -612,18 +608,91 @@ int dcreg_set_target(dcreg_ctx* ctx, const float* xyz, int64_t m, int stride, do
         CK(cudaMemsetAsync(g.keys, 0xff, (size_t)cap * sizeof(unsigned long long), ctx->stream));
         CK(cudaMemsetAsync(g.hcount, 0, (size_t)cap * sizeof(int), ctx->stream));
         CK(cudaMemsetAsync(fill, 0, (size_t)cap * sizeof(int), ctx->stream));
-        corr::grid_insert_hash_kernel<<<nb, 256, 0, ctx->stream>>>(ctx->d_tgt, (int)m, g, pt_cell);
-        if ((rc = device_exclusive_scan(ctx, g.hcount, cap, g.hstart))) return rc;
-        corr::grid_scatter_kernel<<<nb, 256, 0, ctx->stream>>>(ctx->d_tgt, (int)m, pt_cell, g.hstart, fill, g.pts, 0);
+        corr::grid_insert_hash_kernel<<<nb, 256, 0, ctx->stream>>>(d_pts, (int)m, g, pt_cell);
+        rc = device_exclusive_scan(ctx, g.hcount, cap, g.hstart);
+        corr::grid_scatter_kernel<<<nb, 256, 0, ctx->stream>>>(d_pts, (int)m, pt_cell, g.hstart, fill, g.pts, 0);
         corr::grid_sort_cells_kernel<<<(cap + 255) / 256, 256, 0, ctx->stream>>>(g.pts, g.hstart, g.hcount, nullptr, cap);
         ctx->launches += 3;
         e = cudaStreamSynchronize(ctx->stream);
     }
     cudaFree(pt_cell); cudaFree(fill);
     if (counts) cudaFree(counts);
-    if (e != cudaSuccess) { ctx->err = std::string("grid build: ") + cudaGetErrorString(e); return DCREG_CUDA_ERROR; }
+    if (rc) { free_grid(&g); return rc; }
+    if (e != cudaSuccess) { free_grid(&g); ctx->err = std::string("grid build: ") + cudaGetErrorString(e); return DCREG_CUDA_ERROR; }
     CK(cudaGetLastError());
+    *gout = g;
+    return DCREG_OK;
+}
+
+int dcreg_set_target(dcreg_ctx* ctx, const float* xyz, int64_t m, int stride, double cell_size) {
+    if (!ctx) return DCREG_BAD_ARG;
+    if (!xyz || m <= 0 || stride < 3 || !(cell_size > 0.0) || m > 0x7fffffffLL) {
+        ctx->err = "dcreg_set_target: empty cloud, stride < 3, cell_size <= 0 or too many points";
+        return DCREG_BAD_ARG;
+    }
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->d_tgt) cudaFree(ctx->d_tgt);
+    ctx->d_tgt = nullptr;
+    free_grid(&ctx->grid);
+    ctx->has_grid = false;
+    CK(cudaMalloc(&ctx->d_tgt, (size_t)m * sizeof(float4)));
+    ctx->n_tgt = m;
+    int rc = upload_points(ctx, xyz, m, stride, ctx->d_tgt);
+    if (rc) return rc;
+    ctx->cell_size = cell_size;
+    if ((rc = build_grid(ctx, ctx->d_tgt, m, cell_size, &ctx->grid, &ctx->grid_cells))) return rc;
     ctx->has_grid = true;
+    return DCREG_OK;
+}
+
+// Post-run point-to-point metrics, replaces calculatePointToPointError (DCReg/include/utils.hpp:538-589; called at
+// icp_test_runner.cpp:506-510 and once per CSV row at :1463-1470): forward exact 1-NN aligned source -> target
+// (RMSE over ALL source points of the distances below the threshold, fitness, mean distance), backward exact 1-NN
+// target -> aligned source, Chamfer = mean of the two mean distances.  out = { rmse, fitness, chamfer, n_valid }.
+int dcreg_point_to_point_metrics(dcreg_ctx* ctx, const double T[16], double error_threshold, double out[4]) {
+    if (!ctx) return DCREG_BAD_ARG;
+    if (!T || !out) { ctx->err = "p2p metrics: null pointer"; return DCREG_BAD_ARG; }
+    if (!ctx->d_src || !ctx->has_grid || !ctx->d_tgt) { ctx->err = "p2p metrics: set source and target first"; return DCREG_BAD_ARG; }
+    if (!ctx->grid.dense) { ctx->err = "p2p metrics need the dense grid (target bounding box too large for this cell size)"; return DCREG_BAD_ARG; }
+    CK(cudaSetDevice(ctx->device));
+    const long long n = ctx->n_src, m = ctx->n_tgt;
+    double* dT = ctx->d_small + 640;
+    CK(cudaMemcpyAsync(dT, T, 12 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    const int gridf = stream_grid(ctx, n, 8), gridb = stream_grid(ctx, m, 8);
+    int rc = ensure_partials(ctx, gridf > gridb ? gridf : gridb);
+    if (rc) return rc;
+    std::vector<double> hp((size_t)3 * (gridf > gridb ? gridf : gridb));
+    // forward
+    corr::nn1_metrics_kernel<<<gridf, kBlock, 0, ctx->stream>>>(ctx->d_src, n, dT, ctx->grid, error_threshold, ctx->d_partials);
+    ctx->launches++;
+    CK(cudaMemcpyAsync(hp.data(), ctx->d_partials, (size_t)3 * gridf * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    double sum_fwd = 0, sum_sq = 0, valid = 0;
+    for (int b = 0; b < gridf; ++b) { sum_fwd += hp[3 * b]; sum_sq += hp[3 * b + 1]; valid += hp[3 * b + 2]; }
+    // backward: grid over the aligned source
+    float4* d_aligned = nullptr;
+    CK(cudaMalloc(&d_aligned, (size_t)n * sizeof(float4)));
+    corr::transform_points_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_src, n, dT, d_aligned);
+    ctx->launches++;
+    corr::Grid ga{};
+    rc = build_grid(ctx, d_aligned, n, ctx->cell_size, &ga, nullptr);
+    if (rc == DCREG_OK && !ga.dense) { rc = DCREG_BAD_ARG; ctx->err = "p2p metrics: aligned cloud spans too many cells"; }
+    double sum_bwd = 0;
+    if (rc == DCREG_OK) {
+        corr::nn1_metrics_kernel<<<gridb, kBlock, 0, ctx->stream>>>(ctx->d_tgt, m, nullptr, ga, error_threshold, ctx->d_partials);
+        ctx->launches++;
+        cudaMemcpyAsync(hp.data(), ctx->d_partials, (size_t)3 * gridb * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+        cudaError_t e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) { rc = DCREG_CUDA_ERROR; ctx->err = cudaGetErrorString(e); }
+        for (int b = 0; b < gridb; ++b) sum_bwd += hp[3 * b];
+    }
+    free_grid(&ga);
+    cudaFree(d_aligned);
+    if (rc) return rc;
+    out[0] = sqrt(sum_sq / (double)n);
+    out[1] = valid / (double)n;
+    out[2] = 0.5 * (sum_fwd / (double)n + sum_bwd / (double)m);
+    out[3] = valid;
     return DCREG_OK;
 }
 

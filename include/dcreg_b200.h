@@ -205,6 +205,12 @@ int dcreg_icp_run_host_planes(dcreg_ctx* ctx, const dcreg_icp_params* params,
  * eigenvalue floor, or 1e6*I when not converged.  cov: 36 doubles. */
 int dcreg_last_covariance(dcreg_ctx* ctx, double cov[36]);
 
+/* Post-run point-to-point metrics on the device.  Replaces calculatePointToPointError
+ * (DCReg/include/utils.hpp:538-589; callers icp_test_runner.cpp:506-510 and :1463-1470): aligned = fl32(T * source);
+ * out = { P2P RMSE (over all source points, distances below error_threshold), P2P fitness, Chamfer distance,
+ * number of source points within the threshold }.  Needs dcreg_set_source + dcreg_set_target. */
+int dcreg_point_to_point_metrics(dcreg_ctx* ctx, const double T[16], double error_threshold, double out[4]);
+
 /* ---- multi-GPU: point-block sharding ---------------------------------------
  * Each rank holds a contiguous block of source slots; after K1 the 27+3 accumulators are summed
  * over ranks (one ncclAllReduce of 30 doubles on the context's stream), then every rank runs K2

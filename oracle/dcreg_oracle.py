@@ -527,3 +527,30 @@ def icp_so3(src_f32, tgt_f32, T_init, prm: Params, tree=None):
             break
     T = np.eye(4); T[:3, :3] = R; T[:3, 3] = t
     return converged, T, logs, status
+
+
+# ----------------------------------------------------------------------------
+# Post-run metrics
+# ----------------------------------------------------------------------------
+def point_to_point_metrics(src_f32, tgt_f32, T, error_threshold, tree_tgt=None):
+    """calculatePointToPointError, DCReg/include/utils.hpp:538-589 (+ pcl::transformPointCloud: FP64 math, float32
+    store).  Returns dict(rmse, fitness, chamfer, n_valid).  FLANN reports float32 squared distances."""
+    from scipy.spatial import cKDTree
+    aligned = transform_points_f32(src_f32, T[:3, :3], T[:3, 3])
+    if tree_tgt is None:
+        tree_tgt = build_tree(tgt_f32)
+
+    def nn_d2(tree, data_f32, queries_f32):
+        _, idx = tree.query(queries_f32.astype(np.float64), k=1)
+        e = queries_f32 - data_f32[idx]                              # float32 differences
+        return (e[:, 0] * e[:, 0] + e[:, 1] * e[:, 1] + e[:, 2] * e[:, 2]).astype(np.float32)
+
+    d2 = nn_d2(tree_tgt, tgt_f32, aligned).astype(np.float64)
+    dist = np.sqrt(d2)
+    ok = dist < error_threshold
+    n = len(aligned)
+    rmse = math.sqrt(float(d2[ok].sum()) / n)
+    fitness = float(ok.sum()) / n
+    d2b = nn_d2(cKDTree(aligned.astype(np.float64)), aligned, tgt_f32).astype(np.float64)
+    chamfer = 0.5 * (float(dist.sum()) / n + float(np.sqrt(d2b).sum()) / len(tgt_f32))
+    return {"rmse": rmse, "fitness": fitness, "chamfer": chamfer, "n_valid": int(ok.sum())}

@@ -412,6 +412,23 @@ def test_icp_monte_carlo_trials_c5(ctx, cylinder):
     sc.close()
 
 
+@pytest.mark.parametrize("thr", [0.2, 0.03])
+def test_point_to_point_metrics_device(ctx, golden, cylinder, tree, thr):
+    """Device P2P RMSE / fitness / Chamfer (exact 1-NN both ways) against the oracle and the shipped summary."""
+    g = golden["G2"]
+    conv, T, logs, status = o.icp_so3(cylinder, cylinder, init_T(g["setup"]), params_from(g["setup"], "Ours"), tree)
+    ctx.set_source(cylinder); ctx.set_target(cylinder, 1.0)
+    for Tm in (T, init_T(g["setup"]), o.pose6d_to_matrix(30.0, -5.0, 2.0, 0.0, 0.0, 0.3)):   # aligned, initial, far away
+        ref = o.point_to_point_metrics(cylinder, cylinder, Tm, thr, tree)
+        got = ctx.point_to_point_metrics(Tm, thr)
+        assert got["n_valid"] == ref["n_valid"]
+        assert abs(got["rmse"] - ref["rmse"]) < 1e-9 and abs(got["chamfer"] - ref["chamfer"]) < 1e-9
+        assert abs(got["fitness"] - ref["fitness"]) < 1e-12
+    if thr == 0.2:
+        got = ctx.point_to_point_metrics(T, thr)
+        assert abs(got["rmse"] - 0.036217) < 2e-6 and abs(got["chamfer"] - 0.032915) < 2e-6
+
+
 def test_icp_abort_not_enough_points(ctx, cylinder):
     from dcreg_b200 import api
     far = o.pose6d_to_matrix(500.0, 0, 0, 0, 0, 0)

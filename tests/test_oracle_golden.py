@@ -143,3 +143,13 @@ def test_reduce_seam_equals_loop_stages(cylinder, tree, golden):
     out27, stats = o.reduce_normal_equations(src4, frozen, T0[:3, :3], T0[:3, 3], True)
     assert np.allclose(out27, o.pack27(H, gg), rtol=1e-13, atol=1e-12)
     assert int(stats[1]) == int(corr.valid.sum())
+
+
+def test_point_to_point_metrics_match_shipped_summary(golden, cylinder, tree):
+    """statistics_summary.txt of G2 ("Ours"): P2P RMSE 0.036217, P2P fitness 100 % (7562), Chamfer 0.032915;
+    error_threshold = 0.2 (icp.yaml icp.error_threshold)."""
+    g = golden["G2"]
+    conv, T, logs, status = o.icp_so3(cylinder, cylinder, init_T(g["setup"]), params_from(g["setup"], "Ours"), tree)
+    m = o.point_to_point_metrics(cylinder, cylinder, T, 0.2, tree)
+    assert abs(m["rmse"] - 0.036217) < 2e-6 and abs(m["chamfer"] - 0.032915) < 2e-6
+    assert m["n_valid"] == 7562 and m["fitness"] == 1.0
