@@ -88,7 +88,7 @@ EXPORTS = [
     "dcreg_reduce_normal_equations_host", "dcreg_analyze_and_solve", "dcreg_solve_pcg", "dcreg_icp_run",
     "dcreg_icp_run_host_planes", "dcreg_last_covariance", "dcreg_point_to_point_metrics", "dcreg_comm_unique_id", "dcreg_comm_init",
     "dcreg_comm_destroy", "dcreg_set_global_source_count", "dcreg_launch_count", "dcreg_device_source",
-    "dcreg_device_planes_f64", "dcreg_device_planes_f32", "dcreg_freeze_planes_f32", "dcreg_time_reduce",
+    "dcreg_device_planes_f64", "dcreg_device_planes_f32", "dcreg_freeze_planes_f32", "dcreg_time_reduce", "dcreg_time_iteration",
 ]
 
 
@@ -132,6 +132,7 @@ def load_library():
         getattr(lib, nm).argtypes = [vp]; getattr(lib, nm).restype = vp
     lib.dcreg_freeze_planes_f32.argtypes = [vp]
     lib.dcreg_time_reduce.argtypes = [vp, ci, dp, ci, ci, ci, C.POINTER(C.c_float)]
+    lib.dcreg_time_iteration.argtypes = [vp, C.POINTER(IcpParams), dp, ci, ci, C.POINTER(C.c_float)]
     _lib = lib
     return lib
 
@@ -277,6 +278,12 @@ class Context:
         prt = pose_Rt(T)
         self._check(self.lib.dcreg_time_reduce(self._h, int(plane_is_f64), _dptr(prt), int(bool(use_weight_derivative)),
                                                reps, int(flush_l2), C.byref(ms)))
+        return float(ms.value)
+
+    def time_iteration(self, params: IcpParams, T, what: int, reps: int) -> float:
+        ms = C.c_float(0)
+        T = np.ascontiguousarray(T, dtype=np.float64)
+        self._check(self.lib.dcreg_time_iteration(self._h, C.byref(params), _dptr(T), int(what), int(reps), C.byref(ms)))
         return float(ms.value)
 
     def analyze_and_solve(self, H27, params: IcpParams):

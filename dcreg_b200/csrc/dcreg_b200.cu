@@ -69,6 +69,10 @@ struct IterArgs {
     double* acc;
     double4* planes_out;      // optional: materialise the planes at the ORIGINAL slot index (seam 1)
     dcreg_icp_params prm;
+    const int4* nn;           // kPreNN: records from corr::knn5_kernel (corr::kKnnRec int4 per source slot)
+    double4* plane_cache;     // kPreNN: plane fitted to the slot's current neighbour list (reused while the list stays)
+    signed char* fit_state;   // kPreNN: 0 = nothing cached, 1 = cached fit failed its gates, 2 = cached plane valid
+    int debug;                // profiling only (tools/prof_iter.py): 1 = no plane fit, 2 = no search either, 3 = exit before the grid reduction
 };
 
 struct IterSmem {
@@ -79,7 +83,8 @@ struct IterSmem {
 // One ICP iteration on the device: stage S1 (correspondences: exact 5-NN in the grid, plane fit, gates) fused with
 // the residual / weight / Jacobian row and the Gram accumulation (S4-S5).  One source point per thread per trip;
 // no per-thread accumulator block: the 8x8 Gram is accumulated with DMMA (two registers per lane).
-template <bool kUseWd>
+// kPreNN: the neighbours come from corr::knn5_kernel (dense grid) instead of the in-thread search (hash grid, seam 1).
+template <bool kUseWd, bool kPreNN>
 __global__ void __launch_bounds__(kBlock, 3) icp_iteration_kernel(const __grid_constant__ IterArgs a) {
     __shared__ IterSmem sm;
     if (a.state->done) return;
@@ -102,11 +107,36 @@ __global__ void __launch_bounds__(kBlock, 3) icp_iteration_kernel(const __grid_c
             const float qz = (float)(P.R[6] * px + P.R[7] * py + P.R[8] * pz + P.t[2]);
             corr::Knn5 nn;
             corr::knn_init(nn);
-            corr::knn_search(a.grid, qx, qy, qz, nn);
+            bool same_list = false;
+            if (kPreNN) {
+                const int4 n0 = __ldg(&a.nn[corr::kKnnRec * i]), n1 = __ldg(&a.nn[corr::kKnnRec * i + 1]);
+                nn.pos[0] = n0.x; nn.pos[1] = n0.y; nn.pos[2] = n0.z; nn.pos[3] = n0.w; nn.pos[4] = n1.x;
+                nn.d2[4] = __int_as_float(n1.y);
+                same_list = (n1.w & 1) != 0;
+            } else if (a.debug != 2) {
+                corr::knn_search(a.grid, qx, qy, qz, nn);
+            }
+            int fit = 0;                                                      // 1 = gates failed, 2 = plane valid
+            if (nn.pos[4] >= 0 && (kPreNN || (double)nn.d2[4] < r2max)) {
+                // the fit depends only on the five target points and their order: reuse it while the list stays
+                const int cached = (kPreNN && same_list) ? (int)a.fit_state[i] : 0;
+                if (cached == 2) {
+                    const double4 c = a.plane_cache[i];
+                    nx = c.x; ny = c.y; nz = c.z; d = c.w;
+                    fit = 2;
+                } else if (cached == 1) {
+                    fit = 1;
+                } else if (a.debug != 1) {
+                    fit = corr::fit_plane(a.grid, nn, a.prm.min_normal_norm, a.prm.plane_thickness, nx, ny, nz, d) ? 2 : 1;
+                    if (kPreNN && fit == 2) a.plane_cache[i] = make_double4(nx, ny, nz, d);
+                }
+            }
+            if (kPreNN) a.fit_state[i] = (signed char)fit;
             if (nn.pos[4] >= 0 && (double)nn.d2[4] < r2max) {                // icp_test_runner.cpp:1726
                 npt += 1;                                                     // :1731
-                ok = corr::fit_plane(a.grid, nn, a.prm.min_normal_norm, a.prm.plane_thickness, nx, ny, nz, d);
+                ok = fit == 2;
             }
+            if (!ok) { nx = 0.0; ny = 0.0; nz = 0.0; d = 0.0; }
             if (a.planes_out)
                 a.planes_out[__float_as_int(p4.w)] = ok ? make_double4(nx, ny, nz, d) : make_double4(0.0, 0.0, 0.0, 0.0);
         }
@@ -115,6 +145,7 @@ __global__ void __launch_bounds__(kBlock, 3) icp_iteration_kernel(const __grid_c
         __syncwarp();
         k1::gram_accumulate_dmma(sm.tbuf[warp], lane, c, c0, c1, e0, e1);
     }
+    if (a.debug == 3) { if (c0 + e0 == 1.2345) a.acc[0] = c1 + e1; return; }
     k1::finish_block(c0 + e0, c1 + e1, neff, npt, sm.gram, a.partials, a.counter, a.state->R, a.acc);
 }
 
@@ -266,6 +297,8 @@ struct dcreg_ctx {
 
     float4* d_tgt = nullptr; long long n_tgt = 0;
     corr::Grid grid{}; long long grid_cells = 0; bool has_grid = false;
+    double4* d_plane_cache = nullptr; signed char* d_fit_state = nullptr;   // plane of the slot's current neighbour list
+    int4* d_nn = nullptr; long long nn_cap = 0; bool nn_valid = false;   // neighbours of the sorted source (seeds of the next iteration)
     float4* d_src_sorted = nullptr; long long src_sorted_cap = 0;     // source in target-cell order (w = original index)
     int* d_cell_tmp = nullptr; long long cell_tmp_cap = 0;            // counts / fill cursors for the source sort
     int* d_pt_cell = nullptr; long long pt_cell_cap = 0;
@@ -500,7 +533,7 @@ int dcreg_destroy(dcreg_ctx* ctx) {
     void* ptrs[] = {ctx->d_src, ctx->d_stage, ctx->d_tgt, ctx->grid.keys, ctx->grid.cell_start, ctx->grid.hstart,
                     ctx->grid.hcount, ctx->d_src_sorted, ctx->d_cell_tmp, ctx->d_pt_cell, ctx->d_tile_sums,
                     ctx->grid.pts, ctx->d_planes64, ctx->d_planes32, ctx->d_partials, ctx->d_counter, ctx->d_acc,
-                    ctx->d_state, ctx->d_log, ctx->d_small, ctx->d_analysis, ctx->d_flush};
+                    ctx->d_state, ctx->d_log, ctx->d_small, ctx->d_analysis, ctx->d_flush, ctx->d_nn, ctx->d_plane_cache, ctx->d_fit_state};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
@@ -752,6 +785,7 @@ static int launch_iteration(dcreg_ctx* ctx, const dcreg_icp_params* prm, const f
     a.src = src; a.n = ctx->n_src; a.grid = ctx->grid; a.state = ctx->d_state;
     a.partials = ctx->d_partials; a.counter = ctx->d_counter; a.acc = ctx->d_acc;
     a.planes_out = planes_out; a.prm = *prm;
+    { static int dbg = -1; if (dbg < 0) { const char* e = getenv("DCREG_IT_DEBUG"); dbg = e ? atoi(e) : 0; } a.debug = dbg; }
     {   // rings of cells that cover the search radius (exactness of the 5-NN-within-radius rule)
         const int rings = (int)ceil(prm->search_radius / ctx->cell_size - 1e-9);
         if (rings < 1 || rings > 4) {
@@ -760,14 +794,48 @@ static int launch_iteration(dcreg_ctx* ctx, const dcreg_icp_params* prm, const f
         }
         a.grid.rings = rings;
     }
-    if (prm->use_weight_derivative) icp_iteration_kernel<true><<<grid, kBlock, 0, ctx->stream>>>(a);
-    else icp_iteration_kernel<false><<<grid, kBlock, 0, ctx->stream>>>(a);
+    const bool pre_nn = ctx->grid.dense && !planes_out && ctx->n_src <= 0x1fffffffLL && !getenv("DCREG_FUSED_SEARCH");
+    if (pre_nn) {
+        if (ctx->nn_cap < ctx->n_src) {
+            if (ctx->d_nn) cudaFree(ctx->d_nn);
+            ctx->d_nn = nullptr; ctx->nn_cap = 0;
+            if (ctx->d_plane_cache) cudaFree(ctx->d_plane_cache);
+            if (ctx->d_fit_state) cudaFree(ctx->d_fit_state);
+            ctx->d_plane_cache = nullptr; ctx->d_fit_state = nullptr;
+            CK(cudaMalloc(&ctx->d_nn, (size_t)ctx->n_src * corr::kKnnRec * sizeof(int4)));
+            CK(cudaMalloc(&ctx->d_plane_cache, (size_t)ctx->n_src * sizeof(double4)));
+            CK(cudaMalloc(&ctx->d_fit_state, (size_t)ctx->n_src));
+            ctx->nn_cap = ctx->n_src;
+            ctx->nn_valid = false;
+        }
+        corr::KnnArgs k{};
+        k.src = src; k.n = ctx->n_src; k.grid = a.grid;
+        k.pose_R = ctx->d_state->R; k.pose_t = ctx->d_state->t; k.done = &ctx->d_state->done;
+        k.nn = ctx->d_nn; k.use_seeds = ctx->nn_valid ? 1 : 0;
+        const double r2 = prm->search_radius * prm->search_radius;
+        float r2f = (float)r2;
+        if ((double)r2f < r2) r2f = nextafterf(r2f, INFINITY);
+        k.r2_up = r2f;
+        const long long threads = ctx->n_src * corr::kKnnLanes;
+        const unsigned kb = (unsigned)((threads + corr::kKnnBlock - 1) / corr::kKnnBlock);
+        if (a.grid.rings == 1) corr::knn5_kernel<1><<<kb, corr::kKnnBlock, 0, ctx->stream>>>(k);
+        else corr::knn5_kernel<0><<<kb, corr::kKnnBlock, 0, ctx->stream>>>(k);
+        ctx->launches++;
+        ctx->nn_valid = true;
+        a.nn = ctx->d_nn; a.plane_cache = ctx->d_plane_cache; a.fit_state = ctx->d_fit_state;
+        if (prm->use_weight_derivative) icp_iteration_kernel<true, true><<<grid, kBlock, 0, ctx->stream>>>(a);
+        else icp_iteration_kernel<false, true><<<grid, kBlock, 0, ctx->stream>>>(a);
+    } else {
+        if (prm->use_weight_derivative) icp_iteration_kernel<true, false><<<grid, kBlock, 0, ctx->stream>>>(a);
+        else icp_iteration_kernel<false, false><<<grid, kBlock, 0, ctx->stream>>>(a);
+    }
     ctx->launches++;
     CK(cudaGetLastError());
     return DCREG_OK;
 }
 
 static int init_state(dcreg_ctx* ctx, const double T[16]) {
+    ctx->nn_valid = false;            // a new run: no neighbours of a previous iteration to seed the search with
     CK(cudaMemcpyAsync(ctx->d_small, T, 16 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     init_state_kernel<<<1, 32, 0, ctx->stream>>>(ctx->d_state, ctx->d_small, ctx->n_src_total, ctx->d_counter);
     ctx->launches++;
@@ -908,6 +976,40 @@ int dcreg_time_reduce(dcreg_ctx* ctx, int plane_is_f64, const double pose_Rt[12]
     }
     *ms_per_launch = (float)(total / reps);
     return rc;
+}
+
+int dcreg_time_iteration(dcreg_ctx* ctx, const dcreg_icp_params* params, const double T[16], int what, int reps,
+                         float* ms_per_body) {
+    if (!ctx || !params || !T || reps <= 0 || !ms_per_body) return DCREG_BAD_ARG;
+    if (!ctx->d_src || !ctx->has_grid) { ctx->err = "time_iteration: set source and target first"; return DCREG_BAD_ARG; }
+    CK(cudaSetDevice(ctx->device));
+    dcreg_icp_params prm = *params;
+    prm.fixed_iterations = 1;
+    prm.max_iterations = reps + 8;
+    int rc;
+    if ((rc = init_state(ctx, T))) return rc;
+    const float4* src_iter = ctx->d_src;
+    if ((rc = sort_source_by_cell(ctx, T, &src_iter))) return rc;
+    for (int warm = 0; warm < 2; ++warm)                                   // instruction caches, lazy module load
+        if ((rc = launch_iteration(ctx, &prm, src_iter, nullptr))) return rc;
+    cudaEvent_t b0, b1;
+    CK(cudaEventCreate(&b0)); CK(cudaEventCreate(&b1));
+    CK(cudaEventRecord(b0, ctx->stream));
+    for (int i = 0; i < reps; ++i) {
+        if ((rc = launch_iteration(ctx, &prm, src_iter, nullptr))) return rc;
+        if (what == 1) {
+            if ((rc = nccl_allreduce_acc(ctx))) return rc;
+            k2_step_kernel<<<1, 32, 0, ctx->stream>>>(ctx->d_acc, ctx->d_state, prm, nullptr, 0);
+            ctx->launches++;
+        }
+    }
+    CK(cudaEventRecord(b1, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, b0, b1);
+    cudaEventDestroy(b0); cudaEventDestroy(b1);
+    *ms_per_body = ms / reps;
+    return DCREG_OK;
 }
 
 int dcreg_analyze_and_solve(dcreg_ctx* ctx, const double H27[27], const dcreg_icp_params* params,

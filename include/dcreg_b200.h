@@ -236,6 +236,11 @@ int dcreg_freeze_planes_f32(dcreg_ctx* ctx);
  * If flush_l2 != 0 a >L2-sized buffer is rewritten before every launch (outside the events). */
 int dcreg_time_reduce(dcreg_ctx* ctx, int plane_is_f64, const double pose_Rt[12],
                       int use_weight_derivative, int reps, int flush_l2, float* ms_per_launch);
+/* Profiling aid for the fused loop: enqueue `reps` loop bodies from pose T (source sorted as dcreg_icp_run does) and
+ * return the average device time per body in milliseconds.  what = 0: the iteration kernel alone at the fixed
+ * pose T; what = 1: iteration kernel + solve/update kernel, i.e. `reps` real iterations (no convergence stop). */
+int dcreg_time_iteration(dcreg_ctx* ctx, const dcreg_icp_params* params, const double T[16], int what,
+                         int reps, float* ms_per_body);
 
 #ifdef __cplusplus
 }
