@@ -88,7 +88,7 @@ EXPORTS = [
     "dcreg_reduce_normal_equations_host", "dcreg_analyze_and_solve", "dcreg_solve_pcg", "dcreg_icp_run",
     "dcreg_icp_run_host_planes", "dcreg_last_covariance", "dcreg_point_to_point_metrics", "dcreg_comm_unique_id", "dcreg_comm_init",
     "dcreg_comm_destroy", "dcreg_set_global_source_count", "dcreg_launch_count", "dcreg_device_source",
-    "dcreg_device_planes_f64", "dcreg_device_planes_f32", "dcreg_freeze_planes_f32", "dcreg_time_reduce", "dcreg_time_iteration",
+    "dcreg_device_planes_f64", "dcreg_device_planes_f32", "dcreg_freeze_planes_f32", "dcreg_time_reduce", "dcreg_time_iteration", "dcreg_iteration_counters",
 ]
 
 
@@ -133,6 +133,7 @@ def load_library():
     lib.dcreg_freeze_planes_f32.argtypes = [vp]
     lib.dcreg_time_reduce.argtypes = [vp, ci, dp, ci, ci, ci, C.POINTER(C.c_float)]
     lib.dcreg_time_iteration.argtypes = [vp, C.POINTER(IcpParams), dp, ci, ci, C.POINTER(C.c_float)]
+    lib.dcreg_iteration_counters.argtypes = [vp, ci, C.POINTER(C.c_uint64)]
     _lib = lib
     return lib
 
@@ -285,6 +286,11 @@ class Context:
         T = np.ascontiguousarray(T, dtype=np.float64)
         self._check(self.lib.dcreg_time_iteration(self._h, C.byref(params), _dptr(T), int(what), int(reps), C.byref(ms)))
         return float(ms.value)
+
+    def iteration_counters(self, enable: bool = True):
+        out = (C.c_uint64 * 2)()
+        self._check(self.lib.dcreg_iteration_counters(self._h, int(enable), out))
+        return int(out[0]), int(out[1])
 
     def analyze_and_solve(self, H27, params: IcpParams):
         """DCReg::analyzeDegeneracy + solveDegenerateSystem on the device.  Returns (Analysis, dx, status)."""

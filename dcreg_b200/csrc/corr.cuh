@@ -353,275 +353,236 @@ __device__ __forceinline__ void knn_search(const Grid& g, float qx, float qy, fl
     }
 }
 
-// ---- cooperative exact 5-NN (dense grid): 8 lanes per query --------------------------------------------------------
-// The fused one-thread-per-query search is latency- and divergence-bound at ICP sizes (100 k queries = 5 warps per SM
-// sub-partition, ~8 k dependent instructions each, most of them sorted-list insertions with 2 of 32 lanes active).
-// Here a query is searched by 8 adjacent lanes:
-//   * bound.  Only points that can be among the five nearest need sorting.  The accept rule needs the five nearest
-//     only if the 5th is inside the search radius, so B = fl_up(radius^2) is always a valid bound; and the previous
-//     iteration's five neighbours of the same source point are five distinct target points, so the largest of their
-//     distances to the new query bounds the new 5th distance from above (inclusive - ties are kept and resolved by
-//     the index rule).  The seeds only provide the bound; the scan itself finds every point again.
-//   * rows.  The (2K+1)^2 cell rows of the neighbourhood (own row first) are set up by the lanes in parallel:
-//     one contiguous point range per row, end cells and whole rows dropped when their box distance exceeds B.
-//   * scan.  The lanes walk the concatenation of the ranges with stride 8 (coalesced 128 B loads, same trip count)
-//     and append every candidate with d2 <= B to a 32-entry shared-memory buffer.
-//   * select.  Rank of an entry = number of entries before it in (d2, index) order; ranks 0..4 are the answer.
-//     If more than 32 candidates survived (no seeds yet: first iteration), B is lowered to the 5th smallest of the
-//     32 buffered ones - again five distinct real points - and the scan is repeated; if that cannot lower B (32+
-//     points tied at the bound) one lane runs the sequential exact search.
-//   * skip.  Every scan also yields a lower bound lb6 on the distance of everything OUTSIDE the five (the 6th
-//     buffered candidate, else the bound itself) and remembers where the query was (q_scan).  Later iterations move the
-//     query by delta = |q - q_scan|; while  max_i |q - nb_i| + delta < lb6  (with margins that dwarf the float32
-//     evaluation error of a squared distance) no outside point can have overtaken a neighbour, so the five are only
-//     re-ranked by their new distances and no cell is touched.  Near convergence almost every query takes this path.
-// Record per query (3 int4): {pos0..pos3}, {pos4, bits(d2 of the 5th), bits(lb6), flags}, {bits(q_scan.xyz), 0};
-// pos = position in g.pts, -1 = none; flags bit 0 = the ordered list equals the previous iteration's (the plane fitted
-// to it can be reused: same five rows in the same order give the same QR bit for bit).
-constexpr int kKnnRec = 3;
-constexpr float kKnnLook = 1.21f;                    // squared-distance look-ahead factor beyond the bound (any value >= 1 is exact)
-constexpr int kKnnLanes = 8;
-constexpr int kKnnCap = 32;
-constexpr int kKnnMaxRows = 81;                     // (2 * 4 + 1)^2: launch_iteration caps the ring count at 4
-constexpr int kKnnBlock = 256;
-constexpr int kKnnGroups = kKnnBlock / kKnnLanes;
+// ---- bounded exact M-NN with a gap certificate (dense grid, one thread per query) ----------------------------------
+// Same traversal as knn_search, three differences:
+//   * it keeps the kSeeds (7) nearest, not 5: the first five are the answer, the extra two widen the certificate below;
+//   * the list starts as sentinels at the caller's bound B (any value >= the true 7th squared distance keeps the
+//     search exact: a candidate with d2 == B and a real index still beats a sentinel), so rows / cells / candidates
+//     beyond B are never touched;
+//   * lb collects a lower bound on the squared distance of every target point that does NOT end up in the list:
+//     the d2 of every rejected or evicted candidate and the box distance of everything pruned.  The caller uses it
+//     to prove, in later iterations, that the seven still contain the five nearest without searching
+//     (icp_iter2_kernel).
+constexpr int kSeeds = 7;
 
-struct KnnArgs {
-    const float4* src;        // queries before the pose (sorted source)
-    long long n;
-    Grid grid;
-    const double* pose_R;     // device pointers into the loop state: R[9] row-major, t[3]
-    const double* pose_t;
-    const int* done;          // loop-state flag: skip when set
-    int4* nn;                 // [kKnnRec n] in: previous record (when use_seeds), out: new record
-    int use_seeds;
-    float r2_up;              // radius^2 rounded up to float
+struct KnnM {
+    float d2[kSeeds];
+    int pos[kSeeds];
+    int idx[kSeeds];
 };
 
-struct KnnGroupSmem {
-    int rs[kKnnMaxRows], re[kKnnMaxRows];           // point range of every row (empty when pruned)
-    float d2[kKnnCap];
-    int pos[kKnnCap], idx[kKnnCap];
-    int cnt;
-    int out[7];                                     // pos0..pos4, bits(d2 of the 5th), bits(d2 of the 6th candidate)
-};
+__device__ __forceinline__ void knnm_insert(KnnM& k, float d2, int pos, int idx) {
+    k.d2[kSeeds - 1] = d2; k.pos[kSeeds - 1] = pos; k.idx[kSeeds - 1] = idx;
+#pragma unroll
+    for (int i = kSeeds - 1; i > 0; --i) {
+        const bool sw = (k.d2[i] < k.d2[i - 1]) || (k.d2[i] == k.d2[i - 1] && k.idx[i] < k.idx[i - 1]);
+        if (sw) {
+            const float td = k.d2[i]; k.d2[i] = k.d2[i - 1]; k.d2[i - 1] = td;
+            const int tp = k.pos[i]; k.pos[i] = k.pos[i - 1]; k.pos[i - 1] = tp;
+            const int ti = k.idx[i]; k.idx[i] = k.idx[i - 1]; k.idx[i - 1] = ti;
+        }
+    }
+}
+
+__device__ __forceinline__ void knn_scan_range_lb(const float4* __restrict__ pts, int s, int e, float qx, float qy,
+                                                  float qz, KnnM& k, float& lb) {
+    constexpr int L = kSeeds - 1;
+    int j = s;
+#pragma unroll 1
+    for (; j + 1 < e; j += 2) {                       // two candidates per trip: both loads in flight
+        const float4 p0 = __ldg(&pts[j]), p1 = __ldg(&pts[j + 1]);
+        const float a0 = dist2(qx, qy, qz, p0), a1 = dist2(qx, qy, qz, p1);
+        const int i0 = __float_as_int(p0.w), i1 = __float_as_int(p1.w);
+        if (a0 < k.d2[L] || (a0 == k.d2[L] && i0 < k.idx[L])) { lb = fminf(lb, k.d2[L]); knnm_insert(k, a0, j, i0); }
+        else lb = fminf(lb, a0);                      // rejected candidates and evicted entries bound the outside
+        if (a1 < k.d2[L] || (a1 == k.d2[L] && i1 < k.idx[L])) { lb = fminf(lb, k.d2[L]); knnm_insert(k, a1, j + 1, i1); }
+        else lb = fminf(lb, a1);
+    }
+    if (j < e) {
+        const float4 p0 = __ldg(&pts[j]);
+        const float a0 = dist2(qx, qy, qz, p0);
+        const int i0 = __float_as_int(p0.w);
+        if (a0 < k.d2[L] || (a0 == k.d2[L] && i0 < k.idx[L])) { lb = fminf(lb, k.d2[L]); knnm_insert(k, a0, j, i0); }
+        else lb = fminf(lb, a0);
+    }
+}
+
+__device__ __forceinline__ void knn_search_lb(const Grid& g, float qx, float qy, float qz, float B, KnnM& k, float& lb) {
+    constexpr int L = kSeeds - 1;
+#pragma unroll
+    for (int i = 0; i < kSeeds; ++i) { k.d2[i] = B; k.pos[i] = -1; k.idx[i] = 0x7fffffff; }
+    const int cx = cell_coord(qx, g.inv_cell), cy = cell_coord(qy, g.inv_cell), cz = cell_coord(qz, g.inv_cell);
+    const int K = g.rings;
+    const float cell = (float)(1.0 / g.inv_cell);
+    const int lx = cx - g.ox, ly = cy - g.oy, lz = cz - g.oz;
+    if (lx + K < 0 || lx - K >= g.nx) return;
+    const float eps = 2e-6f * (fabsf(qx) + fabsf(qy) + fabsf(qz) + cell);
+    const float fx = qx - (float)cx * cell, fy = qy - (float)cy * cell, fz = qz - (float)cz * cell;
+#pragma unroll 1
+    for (int ring = 0; ring <= K; ++ring) {
+        if (ring > 1) {
+            const float m = fmaxf(fminf(fminf(fy, cell - fy), fminf(fz, cell - fz)) + (float)(ring - 1) * cell - eps, 0.0f);
+            if (m * m * 0.99999f > k.d2[L]) { lb = fminf(lb, m * m * 0.99999f); break; }
+        }
+#pragma unroll 1
+        for (int dz = -ring; dz <= ring; ++dz) {
+            const int zz = lz + dz;
+            if (zz < 0 || zz >= g.nz) continue;
+            const float gz = dz == 0 ? 0.0f : fmaxf((dz < 0 ? fz + (float)(-dz - 1) * cell : (cell - fz) + (float)(dz - 1) * cell) - eps, 0.0f);
+            const int stepy = (dz == -ring || dz == ring) ? 1 : 2 * ring;     // only the ring's boundary rows
+#pragma unroll 1
+            for (int dy = -ring; dy <= ring; dy += (stepy > 0 ? stepy : 1)) {
+                const int yy = ly + dy;
+                if (yy < 0 || yy >= g.ny) continue;
+                const float gy = dy == 0 ? 0.0f : fmaxf((dy < 0 ? fy + (float)(-dy - 1) * cell : (cell - fy) + (float)(dy - 1) * cell) - eps, 0.0f);
+                const float row_lb = (gy * gy + gz * gz) * 0.99999f;
+                if (row_lb > k.d2[L]) { lb = fminf(lb, row_lb); continue; }
+                const int* rowp = g.cell_start + (size_t)(zz * g.ny + yy) * g.nx;
+                {
+                    const int x0 = min(max(lx, 0), g.nx), x1 = min(max(lx + 1, 0), g.nx);
+                    knn_scan_range_lb(g.pts, __ldg(rowp + x0), __ldg(rowp + x1), qx, qy, qz, k, lb);
+                }
+                bool left = true, right = true;
+#pragma unroll 1
+                for (int dx = 1; dx <= K; ++dx) {
+                    if (left) {
+                        const float gl = fmaxf(fx + (float)(dx - 1) * cell - eps, 0.0f);
+                        const float b = row_lb + gl * gl * 0.99999f;
+                        if (b <= k.d2[L]) {
+                            const int x0 = min(max(lx - dx, 0), g.nx), x1 = min(max(lx - dx + 1, 0), g.nx);
+                            knn_scan_range_lb(g.pts, __ldg(rowp + x0), __ldg(rowp + x1), qx, qy, qz, k, lb);
+                        } else { lb = fminf(lb, b); left = false; }
+                    }
+                    if (right) {
+                        const float gr = fmaxf((cell - fx) + (float)(dx - 1) * cell - eps, 0.0f);
+                        const float b = row_lb + gr * gr * 0.99999f;
+                        if (b <= k.d2[L]) {
+                            const int x0 = min(max(lx + dx, 0), g.nx), x1 = min(max(lx + dx + 1, 0), g.nx);
+                            knn_scan_range_lb(g.pts, __ldg(rowp + x0), __ldg(rowp + x1), qx, qy, qz, k, lb);
+                        } else { lb = fminf(lb, b); right = false; }
+                    }
+                    if (!left && !right) break;
+                }
+            }
+        }
+    }
+}
 
 __device__ __forceinline__ bool knn_less(float d, int i, float d_ref, int i_ref) {
     return d < d_ref || (d == d_ref && i < i_ref);
 }
 
-// The four groups of a warp run every loop in lock-step (trip counts = the maximum over the groups, work predicated
-// per group): a warp that lets its groups drift apart executes each group's instructions separately (measured: 9 of
-// 32 lanes active on average), which costs more than the idle trips.
-template <int kRings>                                             // 1: cell edge = search radius; 0: 1..4 rings at run time
-__global__ void __launch_bounds__(kKnnBlock) knn5_kernel(const __grid_constant__ KnnArgs a) {
-    __shared__ KnnGroupSmem sm[kKnnGroups];
-    if (*a.done) return;
-    const Grid& g = a.grid;
+// ---- one query, one warp (dense grid) -----------------------------------------------------------------------------
+// Same contract as knn_search_lb, executed by all 32 lanes for ONE query: used when only a few slots of a warp need a
+// search, where the sequential search of one lane would keep the other 31 waiting for ~15 us.  Lanes set up the cell
+// rows in parallel, walk every row with stride 32 (coalesced), compact the candidates with d2 <= B into a 64-entry
+// shared buffer and rank them ((d2, index) order): ranks 0..6 are the list, everything else feeds lb.
+// Returns false (nothing usable) when more than 64 candidates survive the bound; the caller then searches sequentially.
+constexpr int kWarpKnnCap = 64;
+
+struct WarpKnnSmem {
+    int rs[81], re[81];                              // point range per cell row (empty when pruned)
+    float d2[kWarpKnnCap];
+    int pos[kWarpKnnCap], idx[kWarpKnnCap];
+    float od2[kSeeds];
+    int opos[kSeeds], oidx[kSeeds];
+};
+
+__device__ __forceinline__ bool knn_warp_search(const Grid& g, float qx, float qy, float qz, float B, WarpKnnSmem& S,
+                                                KnnM& out, float& lb) {
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
-    const int grp = threadIdx.x / kKnnLanes, sub = threadIdx.x & (kKnnLanes - 1);
-    const int gshift = lane & ~(kKnnLanes - 1);                    // first lane of my group inside the warp
-    const unsigned below = (1u << sub) - 1u;                       // group-relative mask of the lanes before me
-    const long long qi = (long long)blockIdx.x * kKnnGroups + grp;
-    const bool active = qi < a.n;
-    KnnGroupSmem& S = sm[grp];
-    if (sub < 7) S.out[sub] = sub < 5 ? -1 : __float_as_int(3.0e38f);
-    __syncwarp();
-    float qx = 0.f, qy = 0.f, qz = 0.f;
-    if (active) {
-        const float4 p4 = __ldg(&a.src[qi]);
-        const double px = p4.x, py = p4.y, pz = p4.z;
-        // q = fl32(R p + t)  (utils.hpp:630-636), same expression as the fused kernel
-        qx = (float)(a.pose_R[0] * px + a.pose_R[1] * py + a.pose_R[2] * pz + a.pose_t[0]);
-        qy = (float)(a.pose_R[3] * px + a.pose_R[4] * py + a.pose_R[5] * pz + a.pose_t[1]);
-        qz = (float)(a.pose_R[6] * px + a.pose_R[7] * py + a.pose_R[8] * pz + a.pose_t[2]);
-    }
-    // ---- bound from the search radius and from the previous neighbours; skip test
-    float B = a.r2_up;
-    int4 s0 = make_int4(-1, -1, -1, -1), s1 = make_int4(-1, 0, 0, 0);
-    bool skip = false;
-    if (a.use_seeds) {
-        bool have = false;
-        float ds = 0.0f;
-        int mine = -1, mine_idx = 0x7fffffff;
-        float4 qs = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (active) {
-            s0 = a.nn[kKnnRec * qi]; s1 = a.nn[kKnnRec * qi + 1];
-            have = s1.x >= 0;                                      // group-uniform
-            if (have) {
-                const int4 s2 = a.nn[kKnnRec * qi + 2];
-                qs = make_float4(__int_as_float(s2.x), __int_as_float(s2.y), __int_as_float(s2.z), 0.f);
-                if (sub < 5) {
-                    mine = sub == 0 ? s0.x : (sub == 1 ? s0.y : (sub == 2 ? s0.z : (sub == 3 ? s0.w : s1.x)));
-                    const float4 p = __ldg(&g.pts[mine]);
-                    ds = dist2(qx, qy, qz, p);
-                    mine_idx = __float_as_int(p.w);
+    const int K = g.rings, W = 2 * K + 1, nrows = W * W;
+    const float cell = (float)(1.0 / g.inv_cell);
+    const int cx = cell_coord(qx, g.inv_cell), cy = cell_coord(qy, g.inv_cell), cz = cell_coord(qz, g.inv_cell);
+    const int lx = cx - g.ox, ly = cy - g.oy, lz = cz - g.oz;
+    const float eps = 2e-6f * (fabsf(qx) + fabsf(qy) + fabsf(qz) + cell);
+    const float fx = qx - (float)cx * cell, fy = qy - (float)cy * cell, fz = qz - (float)cz * cell;
+    float lbl = lb;                                   // lane-local lower bound of everything this lane drops
+    if (lane < kSeeds) { S.od2[lane] = B; S.opos[lane] = -1; S.oidx[lane] = 0x7fffffff; }
+#pragma unroll 1
+    for (int r = lane; r < nrows; r += 32) {
+        const int rz = r / W;
+        const int dz = rz - K, dy = r - rz * W - K;
+        const int zz = lz + dz, yy = ly + dy;
+        int s = 0, e = 0;
+        if (zz >= 0 && zz < g.nz && yy >= 0 && yy < g.ny) {
+            const float gz = dz == 0 ? 0.0f : fmaxf((dz < 0 ? fz + (float)(-dz - 1) * cell : (cell - fz) + (float)(dz - 1) * cell) - eps, 0.0f);
+            const float gy = dy == 0 ? 0.0f : fmaxf((dy < 0 ? fy + (float)(-dy - 1) * cell : (cell - fy) + (float)(dy - 1) * cell) - eps, 0.0f);
+            const float row_lb = (gy * gy + gz * gz) * 0.99999f;
+            if (row_lb <= B) {
+                int xa = lx - K, xb = lx + K;                  // drop end cells whose box distance exceeds the bound
+#pragma unroll 1
+                for (; xa < lx; ++xa) {
+                    const float gl = fmaxf(fx + (float)(lx - xa - 1) * cell - eps, 0.0f);
+                    const float b = row_lb + gl * gl * 0.99999f;
+                    if (b <= B) break;
+                    lbl = fminf(lbl, b);
                 }
-            }
-        }
-        const float dmine = ds;
-#pragma unroll
-        for (int off = 1; off < kKnnLanes; off <<= 1) ds = fmaxf(ds, __shfl_xor_sync(full, ds, off));
-        if (have) {
-            // scan a little beyond the five (10 % in distance): that is what finds the 6th candidate / a gap to it
-            B = fminf(B, ds * kKnnLook);
-            // nothing outside the five was closer than sqrt(lb6) to q_scan; it is now at least sqrt(lb6) - delta away
-            const float ex = qx - qs.x, ey = qy - qs.y, ez = qz - qs.z;
-            const float delta = sqrtf(ex * ex + ey * ey + ez * ez);
-            const float lb6 = sqrtf(__int_as_float(s1.z));
-            skip = (sqrtf(ds) + delta) * 1.00002f + 1e-7f < lb6 * 0.99998f && ds < a.r2_up;
-        }
-        // re-rank the five by their new distances (index rule on ties); done by every group, used when skip
-        int rank = 0;
-#pragma unroll
-        for (int o = 1; o < 5; ++o) {
-            const int from = gshift + (sub + o) % 5;
-            const float od = __shfl_sync(full, dmine, from);
-            const int oi = __shfl_sync(full, mine_idx, from);
-            rank += knn_less(od, oi, dmine, mine_idx) ? 1 : 0;
-        }
-        if (skip && sub < 5) {
-            S.out[rank] = mine;
-            if (rank == 4) S.out[5] = __float_as_int(dmine);
-        }
-    }
-    // ---- rows: one point range each, own row first; only the non-empty ones are kept (compacted per group)
-    const int K = kRings > 0 ? kRings : g.rings, W = 2 * K + 1, nrows = W * W, centre = (nrows - 1) >> 1;
-    int nr = 0;                                                    // rows of my group (group-uniform)
-    {
-        const float cell = (float)(1.0 / g.inv_cell);
-        const int cx = cell_coord(qx, g.inv_cell), cy = cell_coord(qy, g.inv_cell), cz = cell_coord(qz, g.inv_cell);
-        const int lx = cx - g.ox, ly = cy - g.oy, lz = cz - g.oz;
-        // position inside the own cell; gaps are shrunk by an absolute eps that covers the float rounding of
-        // cx * cell, so a bound can only be too small (it never prunes a hit)
-        const float eps = 2e-6f * (fabsf(qx) + fabsf(qy) + fabsf(qz) + cell);
-        const float fx = qx - (float)cx * cell, fy = qy - (float)cy * cell, fz = qz - (float)cz * cell;
 #pragma unroll 1
-        for (int r0 = 0; r0 < nrows; r0 += kKnnLanes) {
-            const int r = r0 + sub;
-            int s = 0, e = 0;
-            if (active && !skip && r < nrows) {
-                const int rr = r == 0 ? centre : (r == centre ? 0 : r);
-                const int rz = rr / W;
-                const int dz = rz - K, dy = rr - rz * W - K;
-                const int zz = lz + dz, yy = ly + dy;
-                if (zz >= 0 && zz < g.nz && yy >= 0 && yy < g.ny) {
-                    const float gz = dz == 0 ? 0.0f : fmaxf((dz < 0 ? fz + (float)(-dz - 1) * cell : (cell - fz) + (float)(dz - 1) * cell) - eps, 0.0f);
-                    const float gy = dy == 0 ? 0.0f : fmaxf((dy < 0 ? fy + (float)(-dy - 1) * cell : (cell - fy) + (float)(dy - 1) * cell) - eps, 0.0f);
-                    const float row_lb = (gy * gy + gz * gz) * 0.99999f;
-                    if (row_lb <= B) {
-                        int xa = lx - K, xb = lx + K;              // drop end cells whose box distance exceeds the bound
-#pragma unroll 1
-                        for (; xa < lx; ++xa) {
-                            const float gl = fmaxf(fx + (float)(lx - xa - 1) * cell - eps, 0.0f);
-                            if (row_lb + gl * gl * 0.99999f <= B) break;
-                        }
-#pragma unroll 1
-                        for (; xb > lx; --xb) {
-                            const float gr = fmaxf((cell - fx) + (float)(xb - lx - 1) * cell - eps, 0.0f);
-                            if (row_lb + gr * gr * 0.99999f <= B) break;
-                        }
-                        xa = max(xa, 0); xb = min(xb, g.nx - 1);
-                        if (xa <= xb) {
-                            const int* rowp = g.cell_start + (size_t)(zz * g.ny + yy) * g.nx;
-                            s = __ldg(rowp + xa); e = __ldg(rowp + xb + 1);
-                        }
-                    }
+                for (; xb > lx; --xb) {
+                    const float gr = fmaxf((cell - fx) + (float)(xb - lx - 1) * cell - eps, 0.0f);
+                    const float b = row_lb + gr * gr * 0.99999f;
+                    if (b <= B) break;
+                    lbl = fminf(lbl, b);
                 }
-            }
-            const unsigned bits = (__ballot_sync(full, e > s) >> gshift) & 0xffu;
-            if (e > s) { const int at = nr + __popc(bits & below); S.rs[at] = s; S.re[at] = e; }
-            nr += __popc(bits);
-        }
-    }
-    __syncwarp();
-    bool todo = active && !skip;                                   // my group still needs a (further) pass
-    bool slow = false;
-    float lb6 = 0.0f;
-#pragma unroll 1
-    while (__any_sync(full, todo)) {
-        int cnt = 0;                                               // survivors of my group (group-uniform)
-        int nrm = todo ? nr : 0;
-        nrm = max(nrm, __shfl_xor_sync(full, nrm, 8));
-        nrm = max(nrm, __shfl_xor_sync(full, nrm, 16));
-#pragma unroll 1
-        for (int r = 0; r < nrm; ++r) {
-            int j = 0, e = 0;
-            if (todo && r < nr) { j = S.rs[r] + sub; e = S.re[r]; }
-            while (__any_sync(full, j < e)) {
-                bool hit = false;
-                float d = 0.0f;
-                int pi = 0;
-                if (j < e) {
-                    const float4 p = __ldg(&g.pts[j]);
-                    d = dist2(qx, qy, qz, p);
-                    pi = __float_as_int(p.w);
-                    hit = d <= B;
+                xa = max(xa, 0); xb = min(xb, g.nx - 1);
+                if (xa <= xb) {
+                    const int* rowp = g.cell_start + (size_t)(zz * g.ny + yy) * g.nx;
+                    s = __ldg(rowp + xa); e = __ldg(rowp + xb + 1);
                 }
-                const unsigned bits = (__ballot_sync(full, hit) >> gshift) & 0xffu;
-                if (hit) {
-                    const int slot = cnt + __popc(bits & below);
-                    if (slot < kKnnCap) { S.d2[slot] = d; S.pos[slot] = j; S.idx[slot] = pi; }
-                }
-                cnt += __popc(bits);
-                j += kKnnLanes;
-            }
-        }
-        __syncwarp();
-        // ---- ranks of the buffered entries
-        const int m = todo ? min(cnt, kKnnCap) : 0;
-        int mm = m;
-        mm = max(mm, __shfl_xor_sync(full, mm, 8));
-        mm = max(mm, __shfl_xor_sync(full, mm, 16));
-#pragma unroll 1
-        for (int e0 = 0; e0 < mm; e0 += kKnnLanes) {
-            const int e = e0 + sub;
-            const bool mine = e < m;
-            const float de = mine ? S.d2[e] : 0.0f;
-            const int ie = mine ? S.idx[e] : 0;
-            int rank = 0;
-#pragma unroll 1
-            for (int f = 0; f < mm; ++f)
-                if (f < m) rank += knn_less(S.d2[f], S.idx[f], de, ie) ? 1 : 0;
-            if (mine && rank < 5) S.out[rank] = S.pos[e];
-            if (mine && rank == 4) S.out[5] = __float_as_int(de);
-            if (mine && rank == 5) S.out[6] = __float_as_int(de);
-        }
-        __syncwarp();
-        if (todo) {
-            if (cnt <= kKnnCap) {
-                todo = false;
-                // everything outside the five is at least this far (squared): the 6th candidate, else the bound
-                lb6 = cnt >= 6 ? __int_as_float(S.out[6]) : B;
             } else {
-                const float nb = __int_as_float(S.out[5]) * kKnnLook;   // 5th smallest of 32 real points bounds the answer
-                if (nb < B) B = nb;
-                else { slow = true; todo = false; }
+                lbl = fminf(lbl, row_lb);
             }
         }
-        __syncwarp();
+        S.rs[r] = s; S.re[r] = e;
     }
-    if (slow && sub == 0) {                                        // 32+ candidates tied at the bound: sequential exact search
-        Knn5 k;
-        knn_init(k);
-        knn_search(g, qx, qy, qz, k);
-#pragma unroll
-        for (int i = 0; i < 5; ++i) S.out[i] = k.pos[i];
-        S.out[5] = __float_as_int(k.d2[4]);
-        lb6 = 0.0f;                                                // no gap known: the next iteration scans again
-    }
-    if (active && sub == 0) {
-        const int4 o0 = make_int4(S.out[0], S.out[1], S.out[2], S.out[3]);
-        const bool same = a.use_seeds && o0.x == s0.x && o0.y == s0.y && o0.z == s0.z && o0.w == s0.w && S.out[4] == s1.x;
-        a.nn[kKnnRec * qi] = o0;
-        if (skip) {                                                // q_scan and lb6 stay those of the last real scan
-            a.nn[kKnnRec * qi + 1] = make_int4(S.out[4], S.out[5], s1.z, same ? 1 : 0);
-        } else {
-            a.nn[kKnnRec * qi + 1] = make_int4(S.out[4], S.out[5], __float_as_int(lb6), same ? 1 : 0);
-            a.nn[kKnnRec * qi + 2] = make_int4(__float_as_int(qx), __float_as_int(qy), __float_as_int(qz), 0);
+    __syncwarp();
+    int cnt = 0;
+    bool overflow = false;
+#pragma unroll 1
+    for (int r = 0; r < nrows; ++r) {
+        const int e = S.re[r];
+#pragma unroll 1
+        for (int j0 = S.rs[r]; j0 < e; j0 += 32) {
+            const int j = j0 + lane;
+            bool hit = false;
+            float d = 0.0f;
+            int pi = 0;
+            if (j < e) {
+                const float4 p = __ldg(&g.pts[j]);
+                d = dist2(qx, qy, qz, p);
+                pi = __float_as_int(p.w);
+                hit = d <= B;
+                if (!hit) lbl = fminf(lbl, d);
+            }
+            const unsigned bits = __ballot_sync(full, hit);
+            const int slot = cnt + __popc(bits & ((1u << lane) - 1u));
+            if (hit && slot < kWarpKnnCap) { S.d2[slot] = d; S.pos[slot] = j; S.idx[slot] = pi; }
+            cnt += __popc(bits);
         }
+        if (cnt > kWarpKnnCap) { overflow = true; break; }
     }
+    __syncwarp();
+    if (overflow) return false;
+#pragma unroll 1
+    for (int en = lane; en < cnt; en += 32) {
+        const float de = S.d2[en];
+        const int ie = S.idx[en];
+        int rank = 0;
+#pragma unroll 1
+        for (int f = 0; f < cnt; ++f) rank += knn_less(S.d2[f], S.idx[f], de, ie) ? 1 : 0;
+        if (rank < kSeeds) { S.od2[rank] = de; S.opos[rank] = S.pos[en]; S.oidx[rank] = ie; }
+        else lbl = fminf(lbl, de);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) lbl = fminf(lbl, __shfl_xor_sync(full, lbl, off));
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < kSeeds; ++i) { out.d2[i] = S.od2[i]; out.pos[i] = S.opos[i]; out.idx[i] = S.oidx[i]; }
+    lb = lbl;
+    __syncwarp();
+    return true;
 }
 
 // ---- exact 1-NN (post-run point-to-point metrics, DCReg/include/utils.hpp:538-589) ---------------------------
@@ -720,12 +681,12 @@ __global__ void transform_points_kernel(const float4* __restrict__ in, long long
 // Plane through the 5 neighbours: least squares of [nb] x = -1, n = x/|x|, d = 1/|x|, gates
 // |x| >= min_norm and max_j (n.nb_j + d)^2 < thickness^2 (icp_test_runner.cpp:1727-1773).
 // Returns true and (n, d) when a valid plane exists.
-__device__ __forceinline__ bool fit_plane(const Grid& g, const Knn5& k, double min_norm, double thickness,
+__device__ __forceinline__ bool fit_plane(const Grid& g, const int (&kpos)[5], double min_norm, double thickness,
                                           double& nx, double& ny, double& nz, double& d) {
     double A[15], b[5], x[3];
 #pragma unroll
     for (int j = 0; j < 5; ++j) {
-        const float4 p = __ldg(&g.pts[k.pos[j]]);
+        const float4 p = __ldg(&g.pts[kpos[j]]);
         A[j * 3 + 0] = (double)p.x;
         A[j * 3 + 1] = (double)p.y;
         A[j * 3 + 2] = (double)p.z;
@@ -738,7 +699,7 @@ __device__ __forceinline__ bool fit_plane(const Grid& g, const Knn5& k, double m
     double worst = 0.0;
 #pragma unroll
     for (int j = 0; j < 5; ++j) {
-        const float4 p = __ldg(&g.pts[k.pos[j]]);         // re-read (L1 hit) instead of holding 15 more doubles
+        const float4 p = __ldg(&g.pts[kpos[j]]);          // re-read (L1 hit) instead of holding 15 more doubles
         double e = nx * (double)p.x + ny * (double)p.y + nz * (double)p.z + d;
         e *= e;
         worst = fmax(worst, e);

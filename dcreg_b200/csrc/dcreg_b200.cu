@@ -69,10 +69,6 @@ struct IterArgs {
     double* acc;
     double4* planes_out;      // optional: materialise the planes at the ORIGINAL slot index (seam 1)
     dcreg_icp_params prm;
-    const int4* nn;           // kPreNN: records from corr::knn5_kernel (corr::kKnnRec int4 per source slot)
-    double4* plane_cache;     // kPreNN: plane fitted to the slot's current neighbour list (reused while the list stays)
-    signed char* fit_state;   // kPreNN: 0 = nothing cached, 1 = cached fit failed its gates, 2 = cached plane valid
-    int debug;                // profiling only (tools/prof_iter.py): 1 = no plane fit, 2 = no search either, 3 = exit before the grid reduction
 };
 
 struct IterSmem {
@@ -83,8 +79,7 @@ struct IterSmem {
 // One ICP iteration on the device: stage S1 (correspondences: exact 5-NN in the grid, plane fit, gates) fused with
 // the residual / weight / Jacobian row and the Gram accumulation (S4-S5).  One source point per thread per trip;
 // no per-thread accumulator block: the 8x8 Gram is accumulated with DMMA (two registers per lane).
-// kPreNN: the neighbours come from corr::knn5_kernel (dense grid) instead of the in-thread search (hash grid, seam 1).
-template <bool kUseWd, bool kPreNN>
+template <bool kUseWd>
 __global__ void __launch_bounds__(kBlock, 3) icp_iteration_kernel(const __grid_constant__ IterArgs a) {
     __shared__ IterSmem sm;
     if (a.state->done) return;
@@ -107,36 +102,11 @@ __global__ void __launch_bounds__(kBlock, 3) icp_iteration_kernel(const __grid_c
             const float qz = (float)(P.R[6] * px + P.R[7] * py + P.R[8] * pz + P.t[2]);
             corr::Knn5 nn;
             corr::knn_init(nn);
-            bool same_list = false;
-            if (kPreNN) {
-                const int4 n0 = __ldg(&a.nn[corr::kKnnRec * i]), n1 = __ldg(&a.nn[corr::kKnnRec * i + 1]);
-                nn.pos[0] = n0.x; nn.pos[1] = n0.y; nn.pos[2] = n0.z; nn.pos[3] = n0.w; nn.pos[4] = n1.x;
-                nn.d2[4] = __int_as_float(n1.y);
-                same_list = (n1.w & 1) != 0;
-            } else if (a.debug != 2) {
-                corr::knn_search(a.grid, qx, qy, qz, nn);
-            }
-            int fit = 0;                                                      // 1 = gates failed, 2 = plane valid
-            if (nn.pos[4] >= 0 && (kPreNN || (double)nn.d2[4] < r2max)) {
-                // the fit depends only on the five target points and their order: reuse it while the list stays
-                const int cached = (kPreNN && same_list) ? (int)a.fit_state[i] : 0;
-                if (cached == 2) {
-                    const double4 c = a.plane_cache[i];
-                    nx = c.x; ny = c.y; nz = c.z; d = c.w;
-                    fit = 2;
-                } else if (cached == 1) {
-                    fit = 1;
-                } else if (a.debug != 1) {
-                    fit = corr::fit_plane(a.grid, nn, a.prm.min_normal_norm, a.prm.plane_thickness, nx, ny, nz, d) ? 2 : 1;
-                    if (kPreNN && fit == 2) a.plane_cache[i] = make_double4(nx, ny, nz, d);
-                }
-            }
-            if (kPreNN) a.fit_state[i] = (signed char)fit;
+            corr::knn_search(a.grid, qx, qy, qz, nn);
             if (nn.pos[4] >= 0 && (double)nn.d2[4] < r2max) {                // icp_test_runner.cpp:1726
                 npt += 1;                                                     // :1731
-                ok = fit == 2;
+                ok = corr::fit_plane(a.grid, nn.pos, a.prm.min_normal_norm, a.prm.plane_thickness, nx, ny, nz, d);
             }
-            if (!ok) { nx = 0.0; ny = 0.0; nz = 0.0; d = 0.0; }
             if (a.planes_out)
                 a.planes_out[__float_as_int(p4.w)] = ok ? make_double4(nx, ny, nz, d) : make_double4(0.0, 0.0, 0.0, 0.0);
         }
@@ -145,19 +115,250 @@ __global__ void __launch_bounds__(kBlock, 3) icp_iteration_kernel(const __grid_c
         __syncwarp();
         k1::gram_accumulate_dmma(sm.tbuf[warp], lane, c, c0, c1, e0, e1);
     }
-    if (a.debug == 3) { if (c0 + e0 == 1.2345) a.acc[0] = c1 + e1; return; }
     k1::finish_block(c0 + e0, c1 + e1, neff, npt, sm.gram, a.partials, a.counter, a.state->R, a.acc);
+}
+
+// ---- the loop's iteration kernel (dense target grid) -------------------------------------------------------------
+// One thread per source slot (the source is sorted by target cell once per run):
+//   1. q = fl32(R p + t); squared distances from q to the slot's SEVEN nearest target points of its last search.
+//   2. skip test.  That search also left lb8, a lower bound on the squared distance from q_scan (where the query then
+//      was) to every target point outside the seven.  The query has moved by delta = |q - q_scan|; while
+//          (5th smallest of the seven new distances) + delta < sqrt(lb8)
+//      (with margins that dwarf the float32 evaluation error of a squared distance) no outside point can be among
+//      the five nearest, so the seven are only re-ranked by their new distances (index rule on ties) and no cell is
+//      touched.  On a uniform surface the 8th neighbour is ~26 % farther than the 5th, so once the pose moves by
+//      less than a few centimetres per iteration almost every slot takes this path.
+//   3. otherwise an exact bounded 7-NN search (corr::knn_search_lb): bound = 1.21 x the largest of the seven new
+//      distances (seven distinct real points bound the 7th distance; the look-ahead is what finds a gap even when
+//      the 8th candidate is far), or the search radius on the first iteration.
+//   4. neighbour record to HBM (next iteration's seeds); plane fit to the first five, reused while the ordered
+//      list of five stays the same (same five rows in the same order give the same QR bit for bit); residual /
+//      weight / Jacobian row; DMMA Gram accumulation.
+// Tail: packed per-block partial, atomic ticket, last block reduces (k1s::finish_packed).
+// Record per slot (3 int4): {pos0..pos3}, {pos4..pos6, bits(lb8)}, {bits(q_scan.xyz), flags};
+// pos = position in the grid's point array (ascending (d2, index) at the time of writing), -1 = none.
+constexpr int kNnRec = 3;
+constexpr float kNnLook = 1.21f;              // squared-distance look-ahead beyond the seed bound (any value >= 1 is exact)
+constexpr double kCoherentStep = 0.05;        // records are used once no source point moves more than this x search radius per iteration
+constexpr int kCoopMax = 12;                  // up to this many searching slots per warp are searched by the whole warp
+
+struct Iter2Smem {
+    double tbuf[kBlock / 32][8 * k1::kTRow];    // per-warp DMMA transpose buffers (later: the warp's Gram)
+    k1s::TailSmem tail;
+};
+
+struct Iter2Args {
+    IterArgs it;
+    int4* nn;                 // [kNnRec n] neighbour records
+    double4* plane_cache;     // plane fitted to the slot's current neighbour list (reused while the list stays)
+    signed char* fit_state;   // 0 = nothing cached, 1 = cached fit failed its gates, 2 = cached plane valid
+    int* plane_key;           // [5 n] the five positions (ascending) the cached plane was fitted to
+    int coop_max;             // up to this many searching slots per warp are searched by the whole warp, one at a time
+    int force;                // 0: mode and seeds from the loop state (written by K2); 1: coherent mode, seeds = use_seeds
+    int use_seeds;            // (force) records of the previous launch are valid
+    float r2_up;              // search radius^2 rounded up to float
+    unsigned int* stats;      // optional [2]: slots that searched, slots that refitted (profiling)
+};
+
+__device__ __forceinline__ void cswap5(float& da, int& ia, int& pa, float& db, int& ib, int& pb) {
+    if (corr::knn_less(db, ib, da, ia)) {
+        const float td = da; da = db; db = td;
+        const int ti = ia; ia = ib; ib = ti;
+        const int tp = pa; pa = pb; pb = tp;
+    }
+}
+
+template <bool kUseWd>
+__global__ void __launch_bounds__(kBlock, 3) icp_iter2_kernel(const __grid_constant__ Iter2Args a) {
+    __shared__ Iter2Smem sm;
+    const IterArgs& A = a.it;
+    if (A.state->done) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const k1::Pose P = load_pose(A.state);
+    const corr::Grid& g = A.grid;
+    // mode (uniform over the grid): while the pose still moves by more than ~5 % of the search radius per iteration
+    // nothing can be reused; the lean path (plain 5-NN search, no records) is ~25 % cheaper than searching with a
+    // certificate.  K2 flips `coherent` from the size of its update.
+    const bool coherent = a.force ? true : (A.state->coherent != 0);
+    const bool use_seeds = a.force ? (a.use_seeds != 0) : (coherent && A.state->seeds != 0);
+    double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;
+    int neff = 0, npt = 0;
+    unsigned n_search = 0, n_fit = 0;
+    const double r2max = A.prm.search_radius * A.prm.search_radius;
+    const long long n32 = (A.n + 31) & ~31ll;                 // whole warps enter the DMMA section together
+    for (long long i = (long long)blockIdx.x * blockDim.x + tid; i < n32; i += (long long)gridDim.x * blockDim.x) {
+        double px = 0.0, py = 0.0, pz = 0.0, nx = 0.0, ny = 0.0, nz = 0.0, d = 0.0;
+        bool ok = false;
+        corr::KnnM nn;
+        int4 s0 = make_int4(-1, -1, -1, -1), s1 = make_int4(-1, -1, -1, 0), s2 = make_int4(0, 0, 0, 0);
+        bool need = false;
+        float lb = 0.0f, qxs = 0.f, qys = 0.f, qzs = 0.f, Bs = 0.f;
+        if (i < A.n) {
+            const float4 p4 = __ldg(&A.src[i]);
+            px = (double)p4.x; py = (double)p4.y; pz = (double)p4.z;
+            // q = fl32(R p + t)  (utils.hpp:630-636)
+            const float qx = (float)(P.R[0] * px + P.R[1] * py + P.R[2] * pz + P.t[0]);
+            const float qy = (float)(P.R[3] * px + P.R[4] * py + P.R[5] * pz + P.t[1]);
+            const float qz = (float)(P.R[6] * px + P.R[7] * py + P.R[8] * pz + P.t[2]);
+            float B = a.r2_up;
+            need = coherent;
+            if (!coherent) {                              // lean path: plain exact 5-NN, nothing kept
+                corr::Knn5 k5;
+                corr::knn_init(k5);
+                corr::knn_search(g, qx, qy, qz, k5);
+#pragma unroll
+                for (int k = 0; k < 5; ++k) { nn.pos[k] = k5.pos[k]; nn.d2[k] = k5.d2[k]; }
+                nn.pos[5] = -1; nn.pos[6] = -1;
+                ++n_search;
+            }
+            if (use_seeds) {
+                s0 = a.nn[kNnRec * i]; s1 = a.nn[kNnRec * i + 1]; s2 = a.nn[kNnRec * i + 2];
+                if (s1.z >= 0) {                                              // all seven seeds exist
+                    nn.pos[0] = s0.x; nn.pos[1] = s0.y; nn.pos[2] = s0.z; nn.pos[3] = s0.w;
+                    nn.pos[4] = s1.x; nn.pos[5] = s1.y; nn.pos[6] = s1.z;
+#pragma unroll
+                    for (int k = 0; k < corr::kSeeds; ++k) {
+                        const float4 t = __ldg(&g.pts[nn.pos[k]]);
+                        nn.d2[k] = corr::dist2(qx, qy, qz, t);
+                        nn.idx[k] = __float_as_int(t.w);
+                    }
+                    // 16-exchange sorting network on (d2, index)
+#define DCREG_CS(x, y) cswap5(nn.d2[x], nn.idx[x], nn.pos[x], nn.d2[y], nn.idx[y], nn.pos[y])
+                    DCREG_CS(0, 6); DCREG_CS(2, 3); DCREG_CS(4, 5); DCREG_CS(0, 2); DCREG_CS(1, 4); DCREG_CS(3, 6);
+                    DCREG_CS(0, 1); DCREG_CS(2, 5); DCREG_CS(3, 4); DCREG_CS(1, 2); DCREG_CS(4, 6); DCREG_CS(2, 3);
+                    DCREG_CS(4, 5); DCREG_CS(1, 2); DCREG_CS(3, 4); DCREG_CS(5, 6);
+#undef DCREG_CS
+                    B = fminf(B, nn.d2[6] * kNnLook);
+                    const float ex = qx - __int_as_float(s2.x), ey = qy - __int_as_float(s2.y), ez = qz - __int_as_float(s2.z);
+                    const float delta = sqrtf(ex * ex + ey * ey + ez * ez);
+                    lb = __int_as_float(s1.w);
+                    // nothing outside the seven was closer than sqrt(lb) to q_scan; it is now at least sqrt(lb) - delta away
+                    need = !((sqrtf(nn.d2[4]) + delta) * 1.00002f + 1e-7f < sqrtf(lb) * 0.99998f);
+                }
+            }
+            if (need) {
+                s2 = make_int4(__float_as_int(qx), __float_as_int(qy), __float_as_int(qz), 0);
+                ++n_search;
+            }
+            qxs = qx; qys = qy; qzs = qz; Bs = B;
+        }
+        // ---- searches.  Few per warp: the whole warp searches for one slot at a time (a sequential search would
+        // keep 31 lanes waiting for ~15 us); many: every lane searches for itself.
+        {
+            unsigned todo = __ballot_sync(0xffffffffu, need);
+            if (todo != 0u && __popc(todo) <= a.coop_max) {
+                corr::WarpKnnSmem& W = *reinterpret_cast<corr::WarpKnnSmem*>(sm.tbuf[warp]);
+                while (todo) {
+                    const int src = __ffs(todo) - 1;
+                    todo &= todo - 1;
+                    const float wx = __shfl_sync(0xffffffffu, qxs, src), wy = __shfl_sync(0xffffffffu, qys, src);
+                    const float wz = __shfl_sync(0xffffffffu, qzs, src), wB = __shfl_sync(0xffffffffu, Bs, src);
+                    corr::KnnM r;
+                    float lbq = a.r2_up * 0.9999f;        // nothing beyond the rings of cells is closer than the radius
+                    const bool got = corr::knn_warp_search(g, wx, wy, wz, wB, W, r, lbq);
+                    if (got && lane == src) { nn = r; lb = lbq; need = false; }
+                }
+            }
+        }
+        if (i < A.n) {
+            if (need) {
+                lb = a.r2_up * 0.9999f;
+                corr::knn_search_lb(g, qxs, qys, qzs, Bs, nn, lb);
+            }
+            if (coherent) {
+                a.nn[kNnRec * i] = make_int4(nn.pos[0], nn.pos[1], nn.pos[2], nn.pos[3]);
+                a.nn[kNnRec * i + 1] = make_int4(nn.pos[4], nn.pos[5], nn.pos[6], __float_as_int(lb));
+                a.nn[kNnRec * i + 2] = make_int4(s2.x, s2.y, s2.z, 0);
+            }
+            // The plane is fitted to the five points in ascending position order, not in distance order: the least-
+            // squares solution does not depend on the row order (only its last-bit rounding does), and a canonical
+            // order makes the fit a function of the SET of five, which changes far less often than their ranking.
+            int key[5] = {nn.pos[0], nn.pos[1], nn.pos[2], nn.pos[3], nn.pos[4]};
+#define DCREG_CI(x, y) { const int lo = min(key[x], key[y]), hi = max(key[x], key[y]); key[x] = lo; key[y] = hi; }
+            DCREG_CI(0, 1); DCREG_CI(3, 4); DCREG_CI(2, 4); DCREG_CI(2, 3); DCREG_CI(0, 3); DCREG_CI(0, 2);
+            DCREG_CI(1, 4); DCREG_CI(1, 3); DCREG_CI(1, 2);
+#undef DCREG_CI
+            int fit = 0;                                                      // 1 = gates failed, 2 = plane valid
+            if (nn.pos[4] >= 0) {
+                int cached = 0;
+                if (use_seeds) {
+                    const int* kp = a.plane_key + 5 * i;
+                    if (kp[0] == key[0] && kp[1] == key[1] && kp[2] == key[2] && kp[3] == key[3] && kp[4] == key[4])
+                        cached = (int)a.fit_state[i];
+                }
+                if (cached == 2) {
+                    const double4 c = a.plane_cache[i];
+                    nx = c.x; ny = c.y; nz = c.z; d = c.w;
+                    fit = 2;
+                } else if (cached == 1) {
+                    fit = 1;
+                } else {
+                    fit = corr::fit_plane(g, key, A.prm.min_normal_norm, A.prm.plane_thickness, nx, ny, nz, d) ? 2 : 1;
+                    ++n_fit;
+                    if (coherent) {
+                        if (fit == 2) a.plane_cache[i] = make_double4(nx, ny, nz, d);
+                        int* kp = a.plane_key + 5 * i;
+#pragma unroll
+                        for (int k = 0; k < 5; ++k) kp[k] = key[k];
+                    }
+                }
+            }
+            if (coherent) a.fit_state[i] = (signed char)fit;
+            if (nn.pos[4] >= 0 && (double)nn.d2[4] < r2max) {                // icp_test_runner.cpp:1726
+                npt += 1;                                                     // :1731
+                ok = fit == 2;
+            }
+            if (!ok) { nx = 0.0; ny = 0.0; nz = 0.0; d = 0.0; }
+        }
+        double c[8];
+        k1::slot_front<kUseWd>(P, px, py, pz, nx, ny, nz, d, ok, c, neff);
+        __syncwarp();
+        k1::gram_accumulate_dmma(sm.tbuf[warp], lane, c, c0, c1, e0, e1);
+    }
+    if (a.stats) {
+        n_search = __reduce_add_sync(0xffffffffu, n_search);
+        n_fit = __reduce_add_sync(0xffffffffu, n_fit);
+        if (lane == 0 && (n_search | n_fit)) { atomicAdd(&a.stats[0], n_search); atomicAdd(&a.stats[1], n_fit); }
+    }
+    // ---- tail: the warp's 8x8 Gram -> packed totals (k1s::kPk layout), then the grid reduction
+    c0 += e0; c1 += e1;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        neff += __shfl_xor_sync(0xffffffffu, neff, off);
+        npt += __shfl_xor_sync(0xffffffffu, npt, off);
+    }
+    double* G = sm.tbuf[warp];
+    G[2 * lane] = c0; G[2 * lane + 1] = c1;
+    __syncwarp();
+    double mine = 0.0;
+    if (lane < 21) {
+        int i = 0, rem = lane;
+        while (rem >= 6 - i) { rem -= 6 - i; ++i; }
+        const int j = i + rem;
+        mine = 0.5 * (G[i * 8 + j] + G[j * 8 + i]);
+    } else if (lane < 27) {
+        const int i = lane - 21;
+        mine = 0.5 * (G[i * 8 + 6] + G[6 * 8 + i]);
+    } else if (lane == k1s::kPkR2) mine = G[7 * 8 + 7];
+    else if (lane == k1s::kPkB2) mine = G[6 * 8 + 6];
+    else if (lane == k1s::kPkNeff) mine = (double)neff;
+    else if (lane == k1s::kPkNpt) mine = (double)npt;
+    k1s::finish_packed(mine, sm.tail, A.partials, A.counter, A.state->R, A.acc);
 }
 
 // K2 as its own kernel (seam 3, and the sharded loop after the all-reduce).
 __global__ void __launch_bounds__(32) k2_step_kernel(const double* acc, IcpState* st, dcreg_icp_params prm,
-                                                     dcreg_iter_log* log, int log_cap) {
+                                                     dcreg_iter_log* log, int log_cap, const float* src_radius,
+                                                     double coherent_step) {
     __shared__ k2::WarpSmem sm;
     if (st->done) return;
+    // mode of the next iteration kernel: records pay off once no source point moves more than ~5 % of the search radius
+    const double lever = src_radius ? (double)*src_radius : 1.0e30;
+    const double max_step = coherent_step * prm.search_radius;
     if (prm.detection == DCREG_DET_SCHUR_CONDITION_NUMBER && prm.handling == DCREG_HAND_PRECONDITIONED_CG) {
-        k2::icp_step_warp_ours(acc, st, prm, log, log_cap, sm);       // all 32 lanes cooperate
+        k2::icp_step_warp_ours(acc, st, prm, log, log_cap, sm, lever, max_step);   // all 32 lanes cooperate
     } else if (threadIdx.x == 0) {
-        k2::icp_step(acc, st, prm, log, log_cap);                     // baseline methods: generic single-thread path
+        k2::icp_step(acc, st, prm, log, log_cap, lever, max_step);    // baseline methods: generic single-thread path
     }
 }
 
@@ -215,10 +416,21 @@ __global__ void covariance_kernel(const IcpState* st, double* cov) {
         for (int i = 0; i < 36; ++i) cov[i] = (i % 7 == 0) ? 1e6 : 0.0;
 }
 
-__global__ void pack_source_kernel(const float* __restrict__ in, long long n, int stride, float4* __restrict__ out) {
+__global__ void pack_source_kernel(const float* __restrict__ in, long long n, int stride, float4* __restrict__ out,
+                                   float* __restrict__ radius) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    out[i] = make_float4(in[i * stride], in[i * stride + 1], in[i * stride + 2], __int_as_float((int)i));   // w = slot index
+    float r = 0.0f;
+    if (i < n) {
+        const float x = in[i * stride], y = in[i * stride + 1], z = in[i * stride + 2];
+        out[i] = make_float4(x, y, z, __int_as_float((int)i));   // w = slot index
+        r = sqrtf(x * x + y * y + z * z);
+        if (!(r < 3.0e38f)) r = 0.0f;                            // NaN / Inf points do not define a lever arm
+    }
+    if (radius) {                                               // max |p|: lever arm that turns a rotation step into metres
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) r = fmaxf(r, __shfl_xor_sync(0xffffffffu, r, off));
+        if ((threadIdx.x & 31) == 0 && r > 0.0f) atomicMax(reinterpret_cast<int*>(radius), __float_as_int(r));
+    }
 }
 
 __global__ void planes_to_f32_kernel(const double4* __restrict__ in, long long n, float4* __restrict__ out) {
@@ -242,6 +454,7 @@ __global__ void init_state_kernel(IcpState* st, const double* T, long long n_tot
     st->iter = 0; st->done = 0; st->converged = 0; st->status = DCREG_OK;
     for (int i = 0; i < 36; ++i) st->H_last[i] = (i % 7 == 0) ? 1.0 : 0.0;
     st->n_source_total = n_total;
+    st->step_rot = 1.0e30; st->step_trans = 1.0e30; st->seeds = 0; st->coherent_used = 0; st->coherent = 0;
     *counter = 0u;
 }
 
@@ -297,7 +510,11 @@ struct dcreg_ctx {
 
     float4* d_tgt = nullptr; long long n_tgt = 0;
     corr::Grid grid{}; long long grid_cells = 0; bool has_grid = false;
-    double4* d_plane_cache = nullptr; signed char* d_fit_state = nullptr;   // plane of the slot's current neighbour list
+    double4* d_plane_cache = nullptr; signed char* d_fit_state = nullptr;   // plane of the slot's current five neighbours
+    int* d_plane_key = nullptr;                                             // ... and which five (ascending positions)
+    bool force_coherent = false;                                           // profiling (dcreg_time_iteration what = 0)
+    float* d_src_radius = nullptr;                                         // max |p| over the source cloud (device)
+    unsigned int* d_iter_stats = nullptr;                                  // optional profiling counters of the iteration kernel
     int4* d_nn = nullptr; long long nn_cap = 0; bool nn_valid = false;   // neighbours of the sorted source (seeds of the next iteration)
     float4* d_src_sorted = nullptr; long long src_sorted_cap = 0;     // source in target-cell order (w = original index)
     int* d_cell_tmp = nullptr; long long cell_tmp_cap = 0;            // counts / fill cursors for the source sort
@@ -378,7 +595,7 @@ int stream_grid(const dcreg_ctx* ctx, long long n, int per_sm) {
     return (int)(need < cap ? need : cap);
 }
 
-int upload_points(dcreg_ctx* ctx, const float* xyz, long long n, int stride, float4* d_out) {
+int upload_points(dcreg_ctx* ctx, const float* xyz, long long n, int stride, float4* d_out, float* d_radius) {
     const size_t bytes = (size_t)n * stride * sizeof(float);
     if (ctx->stage_bytes < bytes) {
         if (ctx->d_stage) cudaFree(ctx->d_stage);
@@ -387,7 +604,8 @@ int upload_points(dcreg_ctx* ctx, const float* xyz, long long n, int stride, flo
         ctx->stage_bytes = bytes;
     }
     CK(cudaMemcpyAsync(ctx->d_stage, xyz, bytes, cudaMemcpyHostToDevice, ctx->stream));
-    pack_source_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_stage, n, stride, d_out);
+    if (d_radius) CK(cudaMemsetAsync(d_radius, 0, sizeof(float), ctx->stream));
+    pack_source_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_stage, n, stride, d_out, d_radius);
     ctx->launches++;
     CK(cudaGetLastError());
     return DCREG_OK;
@@ -533,7 +751,7 @@ int dcreg_destroy(dcreg_ctx* ctx) {
     void* ptrs[] = {ctx->d_src, ctx->d_stage, ctx->d_tgt, ctx->grid.keys, ctx->grid.cell_start, ctx->grid.hstart,
                     ctx->grid.hcount, ctx->d_src_sorted, ctx->d_cell_tmp, ctx->d_pt_cell, ctx->d_tile_sums,
                     ctx->grid.pts, ctx->d_planes64, ctx->d_planes32, ctx->d_partials, ctx->d_counter, ctx->d_acc,
-                    ctx->d_state, ctx->d_log, ctx->d_small, ctx->d_analysis, ctx->d_flush, ctx->d_nn, ctx->d_plane_cache, ctx->d_fit_state};
+                    ctx->d_state, ctx->d_log, ctx->d_small, ctx->d_analysis, ctx->d_flush, ctx->d_nn, ctx->d_plane_cache, ctx->d_fit_state, ctx->d_iter_stats, ctx->d_src_radius, ctx->d_plane_key};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
@@ -561,7 +779,8 @@ int dcreg_set_source(dcreg_ctx* ctx, const float* xyz, int64_t n, int stride) {
     }
     ctx->n_src = n;
     if (ctx->nranks == 1) ctx->n_src_total = n;
-    return upload_points(ctx, xyz, n, stride, ctx->d_src);
+    if (!ctx->d_src_radius) CK(cudaMalloc(&ctx->d_src_radius, sizeof(float)));
+    return upload_points(ctx, xyz, n, stride, ctx->d_src, ctx->d_src_radius);
 }
 
 int dcreg_set_global_source_count(dcreg_ctx* ctx, int64_t n_total) {
@@ -677,7 +896,7 @@ int dcreg_set_target(dcreg_ctx* ctx, const float* xyz, int64_t m, int stride, do
     ctx->has_grid = false;
     CK(cudaMalloc(&ctx->d_tgt, (size_t)m * sizeof(float4)));
     ctx->n_tgt = m;
-    int rc = upload_points(ctx, xyz, m, stride, ctx->d_tgt);
+    int rc = upload_points(ctx, xyz, m, stride, ctx->d_tgt, nullptr);
     if (rc) return rc;
     ctx->cell_size = cell_size;
     if ((rc = build_grid(ctx, ctx->d_tgt, m, cell_size, &ctx->grid, &ctx->grid_cells))) return rc;
@@ -777,6 +996,12 @@ static int sort_source_by_cell(dcreg_ctx* ctx, const double T[16], const float4*
     return DCREG_OK;
 }
 
+static double coherent_step_setting() {
+    static double v = -1.0;
+    if (v < 0.0) { const char* e = getenv("DCREG_COHERENT_STEP"); v = e ? atof(e) : kCoherentStep; }
+    return v;
+}
+
 static int launch_iteration(dcreg_ctx* ctx, const dcreg_icp_params* prm, const float4* src, double4* planes_out) {
     const int grid = stream_grid(ctx, ctx->n_src, 16);
     int rc = ensure_partials(ctx, grid);
@@ -785,7 +1010,6 @@ static int launch_iteration(dcreg_ctx* ctx, const dcreg_icp_params* prm, const f
     a.src = src; a.n = ctx->n_src; a.grid = ctx->grid; a.state = ctx->d_state;
     a.partials = ctx->d_partials; a.counter = ctx->d_counter; a.acc = ctx->d_acc;
     a.planes_out = planes_out; a.prm = *prm;
-    { static int dbg = -1; if (dbg < 0) { const char* e = getenv("DCREG_IT_DEBUG"); dbg = e ? atoi(e) : 0; } a.debug = dbg; }
     {   // rings of cells that cover the search radius (exactness of the 5-NN-within-radius rule)
         const int rings = (int)ceil(prm->search_radius / ctx->cell_size - 1e-9);
         if (rings < 1 || rings > 4) {
@@ -794,40 +1018,40 @@ static int launch_iteration(dcreg_ctx* ctx, const dcreg_icp_params* prm, const f
         }
         a.grid.rings = rings;
     }
-    const bool pre_nn = ctx->grid.dense && !planes_out && ctx->n_src <= 0x1fffffffLL && !getenv("DCREG_FUSED_SEARCH");
-    if (pre_nn) {
+    const bool fused2 = ctx->grid.dense && !planes_out && ctx->n_src <= 0x1fffffffLL && !getenv("DCREG_FUSED_SEARCH");
+    if (fused2) {
         if (ctx->nn_cap < ctx->n_src) {
             if (ctx->d_nn) cudaFree(ctx->d_nn);
-            ctx->d_nn = nullptr; ctx->nn_cap = 0;
             if (ctx->d_plane_cache) cudaFree(ctx->d_plane_cache);
             if (ctx->d_fit_state) cudaFree(ctx->d_fit_state);
-            ctx->d_plane_cache = nullptr; ctx->d_fit_state = nullptr;
-            CK(cudaMalloc(&ctx->d_nn, (size_t)ctx->n_src * corr::kKnnRec * sizeof(int4)));
+            ctx->d_nn = nullptr; ctx->d_plane_cache = nullptr; ctx->d_fit_state = nullptr; ctx->nn_cap = 0;
+            CK(cudaMalloc(&ctx->d_nn, (size_t)ctx->n_src * kNnRec * sizeof(int4)));
             CK(cudaMalloc(&ctx->d_plane_cache, (size_t)ctx->n_src * sizeof(double4)));
             CK(cudaMalloc(&ctx->d_fit_state, (size_t)ctx->n_src));
+            if (ctx->d_plane_key) cudaFree(ctx->d_plane_key);
+            ctx->d_plane_key = nullptr;
+            CK(cudaMalloc(&ctx->d_plane_key, (size_t)ctx->n_src * 5 * sizeof(int)));
             ctx->nn_cap = ctx->n_src;
             ctx->nn_valid = false;
         }
-        corr::KnnArgs k{};
-        k.src = src; k.n = ctx->n_src; k.grid = a.grid;
-        k.pose_R = ctx->d_state->R; k.pose_t = ctx->d_state->t; k.done = &ctx->d_state->done;
-        k.nn = ctx->d_nn; k.use_seeds = ctx->nn_valid ? 1 : 0;
+        Iter2Args b{};
+        b.it = a;
+        b.nn = ctx->d_nn; b.plane_cache = ctx->d_plane_cache; b.fit_state = ctx->d_fit_state; b.plane_key = ctx->d_plane_key;
+        b.force = ctx->force_coherent ? 1 : 0;
+        { static int cm = -1; if (cm < 0) { const char* e = getenv("DCREG_COOP_MAX"); cm = e ? atoi(e) : kCoopMax; } b.coop_max = cm; }
+        b.use_seeds = ctx->nn_valid ? 1 : 0;
+        b.stats = ctx->d_iter_stats;
         const double r2 = prm->search_radius * prm->search_radius;
         float r2f = (float)r2;
         if ((double)r2f < r2) r2f = nextafterf(r2f, INFINITY);
-        k.r2_up = r2f;
-        const long long threads = ctx->n_src * corr::kKnnLanes;
-        const unsigned kb = (unsigned)((threads + corr::kKnnBlock - 1) / corr::kKnnBlock);
-        if (a.grid.rings == 1) corr::knn5_kernel<1><<<kb, corr::kKnnBlock, 0, ctx->stream>>>(k);
-        else corr::knn5_kernel<0><<<kb, corr::kKnnBlock, 0, ctx->stream>>>(k);
-        ctx->launches++;
+        b.r2_up = r2f;
         ctx->nn_valid = true;
-        a.nn = ctx->d_nn; a.plane_cache = ctx->d_plane_cache; a.fit_state = ctx->d_fit_state;
-        if (prm->use_weight_derivative) icp_iteration_kernel<true, true><<<grid, kBlock, 0, ctx->stream>>>(a);
-        else icp_iteration_kernel<false, true><<<grid, kBlock, 0, ctx->stream>>>(a);
+        const int g2 = stream_grid(ctx, ctx->n_src, 3);
+        if (prm->use_weight_derivative) icp_iter2_kernel<true><<<g2, kBlock, 0, ctx->stream>>>(b);
+        else icp_iter2_kernel<false><<<g2, kBlock, 0, ctx->stream>>>(b);
     } else {
-        if (prm->use_weight_derivative) icp_iteration_kernel<true, false><<<grid, kBlock, 0, ctx->stream>>>(a);
-        else icp_iteration_kernel<false, false><<<grid, kBlock, 0, ctx->stream>>>(a);
+        if (prm->use_weight_derivative) icp_iteration_kernel<true><<<grid, kBlock, 0, ctx->stream>>>(a);
+        else icp_iteration_kernel<false><<<grid, kBlock, 0, ctx->stream>>>(a);
     }
     ctx->launches++;
     CK(cudaGetLastError());
@@ -978,6 +1202,22 @@ int dcreg_time_reduce(dcreg_ctx* ctx, int plane_is_f64, const double pose_Rt[12]
     return rc;
 }
 
+int dcreg_iteration_counters(dcreg_ctx* ctx, int enable, uint64_t out[2]) {
+    if (!ctx || !out) return DCREG_BAD_ARG;
+    CK(cudaSetDevice(ctx->device));
+    out[0] = out[1] = 0;
+    if (ctx->d_iter_stats) {
+        unsigned int h[2] = {0, 0};
+        CK(cudaMemcpyAsync(h, ctx->d_iter_stats, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        out[0] = h[0]; out[1] = h[1];
+    }
+    if (enable && !ctx->d_iter_stats) CK(cudaMalloc(&ctx->d_iter_stats, 2 * sizeof(unsigned int)));
+    if (!enable && ctx->d_iter_stats) { cudaFree(ctx->d_iter_stats); ctx->d_iter_stats = nullptr; }
+    if (ctx->d_iter_stats) CK(cudaMemsetAsync(ctx->d_iter_stats, 0, 2 * sizeof(unsigned int), ctx->stream));
+    return DCREG_OK;
+}
+
 int dcreg_time_iteration(dcreg_ctx* ctx, const dcreg_icp_params* params, const double T[16], int what, int reps,
                          float* ms_per_body) {
     if (!ctx || !params || !T || reps <= 0 || !ms_per_body) return DCREG_BAD_ARG;
@@ -990,8 +1230,9 @@ int dcreg_time_iteration(dcreg_ctx* ctx, const dcreg_icp_params* params, const d
     if ((rc = init_state(ctx, T))) return rc;
     const float4* src_iter = ctx->d_src;
     if ((rc = sort_source_by_cell(ctx, T, &src_iter))) return rc;
+    ctx->force_coherent = (what == 0);                                     // fixed pose: measure the record-reusing mode
     for (int warm = 0; warm < 2; ++warm)                                   // instruction caches, lazy module load
-        if ((rc = launch_iteration(ctx, &prm, src_iter, nullptr))) return rc;
+        if ((rc = launch_iteration(ctx, &prm, src_iter, nullptr))) { ctx->force_coherent = false; return rc; }
     cudaEvent_t b0, b1;
     CK(cudaEventCreate(&b0)); CK(cudaEventCreate(&b1));
     CK(cudaEventRecord(b0, ctx->stream));
@@ -999,10 +1240,11 @@ int dcreg_time_iteration(dcreg_ctx* ctx, const dcreg_icp_params* params, const d
         if ((rc = launch_iteration(ctx, &prm, src_iter, nullptr))) return rc;
         if (what == 1) {
             if ((rc = nccl_allreduce_acc(ctx))) return rc;
-            k2_step_kernel<<<1, 32, 0, ctx->stream>>>(ctx->d_acc, ctx->d_state, prm, nullptr, 0);
+            k2_step_kernel<<<1, 32, 0, ctx->stream>>>(ctx->d_acc, ctx->d_state, prm, nullptr, 0, ctx->d_src_radius, coherent_step_setting());
             ctx->launches++;
         }
     }
+    ctx->force_coherent = false;
     CK(cudaEventRecord(b1, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     float ms = 0.f;
@@ -1073,7 +1315,7 @@ int dcreg_icp_run(dcreg_ctx* ctx, const dcreg_icp_params* params, const double T
         for (int k = 0; k < todo; ++k) {
             if ((rc = launch_iteration(ctx, params, src_iter, nullptr))) return rc;
             if ((rc = nccl_allreduce_acc(ctx))) return rc;          // no-op on one GPU
-            k2_step_kernel<<<1, 32, 0, ctx->stream>>>(ctx->d_acc, ctx->d_state, *params, dlog, log_cap);
+            k2_step_kernel<<<1, 32, 0, ctx->stream>>>(ctx->d_acc, ctx->d_state, *params, dlog, log_cap, ctx->d_src_radius, coherent_step_setting());
             ctx->launches++;
         }
         issued += todo;
@@ -1124,7 +1366,7 @@ int dcreg_icp_run_host_planes(dcreg_ctx* ctx, const dcreg_icp_params* params, co
         if ((rc = launch_reduce(ctx, ctx->d_src, ctx->d_planes64, true, ctx->n_src, &P, params->use_weight_derivative)))
             return rc;
         if ((rc = nccl_allreduce_acc(ctx))) return rc;
-        k2_step_kernel<<<1, 32, 0, ctx->stream>>>(ctx->d_acc, ctx->d_state, *params, dlog, log_cap);
+        k2_step_kernel<<<1, 32, 0, ctx->stream>>>(ctx->d_acc, ctx->d_state, *params, dlog, log_cap, ctx->d_src_radius, coherent_step_setting());
         ctx->launches++;
         CK(cudaMemcpyAsync(hs, ctx->d_state, sizeof(IcpState), cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));

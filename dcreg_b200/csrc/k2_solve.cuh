@@ -31,7 +31,21 @@ struct IcpState {               // device-resident loop state, written only by K
     int status;                 // dcreg_status
     double H_last[36];
     long long n_source_total;   // denominator of fitness (global count when sharded)
+    // temporal coherence of the correspondence stage (dcreg_b200.cu, icp_iter2_kernel): written here by K2
+    double step_rot, step_trans; // |omega| and |v| of the last update
+    int seeds;                  // 1: the iteration kernel that just ran left neighbour records behind
+    int coherent_used;          // mode the iteration kernel that just ran was in (it reads it from `coherent`)
+    int coherent;               // 1: the next iteration may use the records (the last update was small)
 };
+
+// after the pose update: decide the next iteration's mode (see icp_iter2_kernel)
+__device__ __forceinline__ void note_step(IcpState* st, const double* dx, double lever, double max_step) {
+    const double dR = sqrt(dx[0] * dx[0] + dx[1] * dx[1] + dx[2] * dx[2]);
+    const double dT = sqrt(dx[3] * dx[3] + dx[4] * dx[4] + dx[5] * dx[5]);
+    st->step_rot = dR; st->step_trans = dT;
+    st->seeds = st->coherent;                                   // records exist iff the iteration just done was coherent
+    st->coherent = (dR * lever + dT) < max_step ? 1 : 0;         // largest displacement of any source point
+}
 
 __device__ inline void unpack_H(const double* v27, double* H, double* g) {
     int k = 0;
@@ -356,7 +370,7 @@ __device__ __noinline__ void boxplus(double* R, double* t, const double* dx) {
 // One full K2 step on the reduced accumulators: abort rules, analysis, solve, pose update,
 // convergence flag and log record.  Single thread.
 __device__ inline void icp_step(const double* acc, IcpState* st, const dcreg_icp_params& prm,
-                                dcreg_iter_log* log, int log_cap) {
+                                dcreg_iter_log* log, int log_cap, double lever, double max_step) {
     const int iter = st->iter;
     dcreg_iter_log* rec = (log != nullptr && iter < log_cap) ? &log[iter] : nullptr;
     dcreg_analysis scratch;
@@ -396,6 +410,7 @@ __device__ inline void icp_step(const double* acc, IcpState* st, const dcreg_icp
         return;
     }
     boxplus(st->R, st->t, dx);                              // icp_test_runner.cpp:1953
+    note_step(st, dx, lever, max_step);
     {
         double gtmp[6];
         unpack_H(acc, st->H_last, gtmp);                    // matAtA_last, icp_test_runner.cpp:1965
@@ -479,7 +494,7 @@ __device__ __forceinline__ int pcg6_warp(const WarpSmem& sm, int lane, int max_i
 
 // One K2 step by one warp.  Same observable behaviour as icp_step for the "Ours" method.
 __device__ inline void icp_step_warp_ours(const double* acc, IcpState* st, const dcreg_icp_params& prm,
-                                          dcreg_iter_log* log, int log_cap, WarpSmem& sm) {
+                                          dcreg_iter_log* log, int log_cap, WarpSmem& sm, double lever, double max_step) {
     const int lane = threadIdx.x & 31;
     const int iter = st->iter;
     dcreg_iter_log* rec = (log != nullptr && iter < log_cap) ? &log[iter] : nullptr;
@@ -595,6 +610,7 @@ __device__ inline void icp_step_warp_ours(const double* acc, IcpState* st, const
     for (int e = lane; e < 36; e += 32) st->H_last[e] = sm.H[e];     // matAtA_last, icp_test_runner.cpp:1965
     if (lane == 0) {
         boxplus(st->R, st->t, sm.dx);                        // icp_test_runner.cpp:1953
+        note_step(st, sm.dx, lever, max_step);
         const double dR = sqrt(sm.dx[0] * sm.dx[0] + sm.dx[1] * sm.dx[1] + sm.dx[2] * sm.dx[2]);
         const double dT = sqrt(sm.dx[3] * sm.dx[3] + sm.dx[4] * sm.dx[4] + sm.dx[5] * sm.dx[5]);
         st->iter = iter + 1;

@@ -241,6 +241,10 @@ int dcreg_time_reduce(dcreg_ctx* ctx, int plane_is_f64, const double pose_Rt[12]
  * pose T; what = 1: iteration kernel + solve/update kernel, i.e. `reps` real iterations (no convergence stop). */
 int dcreg_time_iteration(dcreg_ctx* ctx, const dcreg_icp_params* params, const double T[16], int what,
                          int reps, float* ms_per_body);
+/* Profiling counters of the loop's iteration kernel since the last call: out = { source slots that ran a neighbour
+ * search, source slots that ran a plane fit } (the others reused the previous iteration's result).
+ * enable != 0 switches the counting on (off by default), 0 switches it off. */
+int dcreg_iteration_counters(dcreg_ctx* ctx, int enable, uint64_t out[2]);
 
 #ifdef __cplusplus
 }
