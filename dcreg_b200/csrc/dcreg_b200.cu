@@ -142,18 +142,28 @@ constexpr float kNnLook = 1.21f;              // squared-distance look-ahead bey
 constexpr double kCoherentStep = 0.05;        // records are used once no source point moves more than this x search radius per iteration
 constexpr int kCoopMax = 12;                  // up to this many searching slots per warp are searched by the whole warp
 
+constexpr int kSearchListMax = 96;            // more searching slots than this in a 256-slot tile: every thread searches for itself
+
 struct Iter2Smem {
-    double tbuf[kBlock / 32][8 * k1::kTRow];    // per-warp DMMA transpose buffers (later: the warp's Gram)
+    double tbuf[kBlock / 32][8 * k1::kTRow];    // per-warp DMMA transpose buffers (also: corr::WarpKnnSmem, the warp's Gram)
     k1s::TailSmem tail;
+    // coherent mode, per 256-slot tile
+    float4 q[kBlock];                           // query (x, y, z), w = search bound B
+    int res[kBlock][10];                        // pos0..pos6, bits(lb), bits(d2 of the 5th), 1 = no search / 0 = searched / 2 = search pending
+    int key[kBlock][5];                         // the five positions, ascending (slots that need a fit)
+    double4 plane[kBlock];
+    signed char fitres[kBlock];
+    int listS[kBlock], listF[kBlock];
+    int nS, nF;
 };
 
 struct Iter2Args {
     IterArgs it;
     int4* nn;                 // [kNnRec n] neighbour records
-    double4* plane_cache;     // plane fitted to the slot's current neighbour list (reused while the list stays)
+    double4* plane_cache;     // plane fitted to the slot's current five neighbours (reused while the set stays)
     signed char* fit_state;   // 0 = nothing cached, 1 = cached fit failed its gates, 2 = cached plane valid
     int* plane_key;           // [5 n] the five positions (ascending) the cached plane was fitted to
-    int coop_max;             // up to this many searching slots per warp are searched by the whole warp, one at a time
+    int coop_max;             // (unused by the tiled path) kept for profiling builds
     int force;                // 0: mode and seeds from the loop state (written by K2); 1: coherent mode, seeds = use_seeds
     int use_seeds;            // (force) records of the previous launch are valid
     float r2_up;              // search radius^2 rounded up to float
@@ -168,9 +178,17 @@ __device__ __forceinline__ void cswap5(float& da, int& ia, int& pa, float& db, i
     }
 }
 
+__device__ __forceinline__ void sort5(int (&key)[5]) {
+#define DCREG_CI(x, y) { const int lo = min(key[x], key[y]), hi = max(key[x], key[y]); key[x] = lo; key[y] = hi; }
+    DCREG_CI(0, 1); DCREG_CI(3, 4); DCREG_CI(2, 4); DCREG_CI(2, 3); DCREG_CI(0, 3); DCREG_CI(0, 2);
+    DCREG_CI(1, 4); DCREG_CI(1, 3); DCREG_CI(1, 2);
+#undef DCREG_CI
+}
+
 template <bool kUseWd>
 __global__ void __launch_bounds__(kBlock, 3) icp_iter2_kernel(const __grid_constant__ Iter2Args a) {
-    __shared__ Iter2Smem sm;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    Iter2Smem& sm = *reinterpret_cast<Iter2Smem*>(smem_raw);
     const IterArgs& A = a.it;
     if (A.state->done) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -185,135 +203,218 @@ __global__ void __launch_bounds__(kBlock, 3) icp_iter2_kernel(const __grid_const
     int neff = 0, npt = 0;
     unsigned n_search = 0, n_fit = 0;
     const double r2max = A.prm.search_radius * A.prm.search_radius;
-    const long long n32 = (A.n + 31) & ~31ll;                 // whole warps enter the DMMA section together
-    for (long long i = (long long)blockIdx.x * blockDim.x + tid; i < n32; i += (long long)gridDim.x * blockDim.x) {
-        double px = 0.0, py = 0.0, pz = 0.0, nx = 0.0, ny = 0.0, nz = 0.0, d = 0.0;
-        bool ok = false;
-        corr::KnnM nn;
-        int4 s0 = make_int4(-1, -1, -1, -1), s1 = make_int4(-1, -1, -1, 0), s2 = make_int4(0, 0, 0, 0);
-        bool need = false;
-        float lb = 0.0f, qxs = 0.f, qys = 0.f, qzs = 0.f, Bs = 0.f;
-        if (i < A.n) {
-            const float4 p4 = __ldg(&A.src[i]);
-            px = (double)p4.x; py = (double)p4.y; pz = (double)p4.z;
-            // q = fl32(R p + t)  (utils.hpp:630-636)
-            const float qx = (float)(P.R[0] * px + P.R[1] * py + P.R[2] * pz + P.t[0]);
-            const float qy = (float)(P.R[3] * px + P.R[4] * py + P.R[5] * pz + P.t[1]);
-            const float qz = (float)(P.R[6] * px + P.R[7] * py + P.R[8] * pz + P.t[2]);
-            float B = a.r2_up;
-            need = coherent;
-            if (!coherent) {                              // lean path: plain exact 5-NN, nothing kept
-                corr::Knn5 k5;
-                corr::knn_init(k5);
-                corr::knn_search(g, qx, qy, qz, k5);
-#pragma unroll
-                for (int k = 0; k < 5; ++k) { nn.pos[k] = k5.pos[k]; nn.d2[k] = k5.d2[k]; }
-                nn.pos[5] = -1; nn.pos[6] = -1;
+    if (!coherent) {
+        // ---- lean mode: one thread per slot, plain exact 5-NN + fit, nothing kept
+        const long long n32 = (A.n + 31) & ~31ll;             // whole warps enter the DMMA section together
+        for (long long i = (long long)blockIdx.x * blockDim.x + tid; i < n32; i += (long long)gridDim.x * blockDim.x) {
+            double px = 0.0, py = 0.0, pz = 0.0, nx = 0.0, ny = 0.0, nz = 0.0, d = 0.0;
+            bool ok = false;
+            if (i < A.n) {
+                const float4 p4 = __ldg(&A.src[i]);
+                px = (double)p4.x; py = (double)p4.y; pz = (double)p4.z;
+                // q = fl32(R p + t)  (utils.hpp:630-636)
+                const float qx = (float)(P.R[0] * px + P.R[1] * py + P.R[2] * pz + P.t[0]);
+                const float qy = (float)(P.R[3] * px + P.R[4] * py + P.R[5] * pz + P.t[1]);
+                const float qz = (float)(P.R[6] * px + P.R[7] * py + P.R[8] * pz + P.t[2]);
+                corr::Knn5 nn;
+                corr::knn_init(nn);
+                corr::knn_search(g, qx, qy, qz, nn);
                 ++n_search;
-            }
-            if (use_seeds) {
-                s0 = a.nn[kNnRec * i]; s1 = a.nn[kNnRec * i + 1]; s2 = a.nn[kNnRec * i + 2];
-                if (s1.z >= 0) {                                              // all seven seeds exist
-                    nn.pos[0] = s0.x; nn.pos[1] = s0.y; nn.pos[2] = s0.z; nn.pos[3] = s0.w;
-                    nn.pos[4] = s1.x; nn.pos[5] = s1.y; nn.pos[6] = s1.z;
-#pragma unroll
-                    for (int k = 0; k < corr::kSeeds; ++k) {
-                        const float4 t = __ldg(&g.pts[nn.pos[k]]);
-                        nn.d2[k] = corr::dist2(qx, qy, qz, t);
-                        nn.idx[k] = __float_as_int(t.w);
-                    }
-                    // 16-exchange sorting network on (d2, index)
-#define DCREG_CS(x, y) cswap5(nn.d2[x], nn.idx[x], nn.pos[x], nn.d2[y], nn.idx[y], nn.pos[y])
-                    DCREG_CS(0, 6); DCREG_CS(2, 3); DCREG_CS(4, 5); DCREG_CS(0, 2); DCREG_CS(1, 4); DCREG_CS(3, 6);
-                    DCREG_CS(0, 1); DCREG_CS(2, 5); DCREG_CS(3, 4); DCREG_CS(1, 2); DCREG_CS(4, 6); DCREG_CS(2, 3);
-                    DCREG_CS(4, 5); DCREG_CS(1, 2); DCREG_CS(3, 4); DCREG_CS(5, 6);
-#undef DCREG_CS
-                    B = fminf(B, nn.d2[6] * kNnLook);
-                    const float ex = qx - __int_as_float(s2.x), ey = qy - __int_as_float(s2.y), ez = qz - __int_as_float(s2.z);
-                    const float delta = sqrtf(ex * ex + ey * ey + ez * ez);
-                    lb = __int_as_float(s1.w);
-                    // nothing outside the seven was closer than sqrt(lb) to q_scan; it is now at least sqrt(lb) - delta away
-                    need = !((sqrtf(nn.d2[4]) + delta) * 1.00002f + 1e-7f < sqrtf(lb) * 0.99998f);
-                }
-            }
-            if (need) {
-                s2 = make_int4(__float_as_int(qx), __float_as_int(qy), __float_as_int(qz), 0);
-                ++n_search;
-            }
-            qxs = qx; qys = qy; qzs = qz; Bs = B;
-        }
-        // ---- searches.  Few per warp: the whole warp searches for one slot at a time (a sequential search would
-        // keep 31 lanes waiting for ~15 us); many: every lane searches for itself.
-        {
-            unsigned todo = __ballot_sync(0xffffffffu, need);
-            if (todo != 0u && __popc(todo) <= a.coop_max) {
-                corr::WarpKnnSmem& W = *reinterpret_cast<corr::WarpKnnSmem*>(sm.tbuf[warp]);
-                while (todo) {
-                    const int src = __ffs(todo) - 1;
-                    todo &= todo - 1;
-                    const float wx = __shfl_sync(0xffffffffu, qxs, src), wy = __shfl_sync(0xffffffffu, qys, src);
-                    const float wz = __shfl_sync(0xffffffffu, qzs, src), wB = __shfl_sync(0xffffffffu, Bs, src);
-                    corr::KnnM r;
-                    float lbq = a.r2_up * 0.9999f;        // nothing beyond the rings of cells is closer than the radius
-                    const bool got = corr::knn_warp_search(g, wx, wy, wz, wB, W, r, lbq);
-                    if (got && lane == src) { nn = r; lb = lbq; need = false; }
-                }
-            }
-        }
-        if (i < A.n) {
-            if (need) {
-                lb = a.r2_up * 0.9999f;
-                corr::knn_search_lb(g, qxs, qys, qzs, Bs, nn, lb);
-            }
-            if (coherent) {
-                a.nn[kNnRec * i] = make_int4(nn.pos[0], nn.pos[1], nn.pos[2], nn.pos[3]);
-                a.nn[kNnRec * i + 1] = make_int4(nn.pos[4], nn.pos[5], nn.pos[6], __float_as_int(lb));
-                a.nn[kNnRec * i + 2] = make_int4(s2.x, s2.y, s2.z, 0);
-            }
-            // The plane is fitted to the five points in ascending position order, not in distance order: the least-
-            // squares solution does not depend on the row order (only its last-bit rounding does), and a canonical
-            // order makes the fit a function of the SET of five, which changes far less often than their ranking.
-            int key[5] = {nn.pos[0], nn.pos[1], nn.pos[2], nn.pos[3], nn.pos[4]};
-#define DCREG_CI(x, y) { const int lo = min(key[x], key[y]), hi = max(key[x], key[y]); key[x] = lo; key[y] = hi; }
-            DCREG_CI(0, 1); DCREG_CI(3, 4); DCREG_CI(2, 4); DCREG_CI(2, 3); DCREG_CI(0, 3); DCREG_CI(0, 2);
-            DCREG_CI(1, 4); DCREG_CI(1, 3); DCREG_CI(1, 2);
-#undef DCREG_CI
-            int fit = 0;                                                      // 1 = gates failed, 2 = plane valid
-            if (nn.pos[4] >= 0) {
-                int cached = 0;
-                if (use_seeds) {
-                    const int* kp = a.plane_key + 5 * i;
-                    if (kp[0] == key[0] && kp[1] == key[1] && kp[2] == key[2] && kp[3] == key[3] && kp[4] == key[4])
-                        cached = (int)a.fit_state[i];
-                }
-                if (cached == 2) {
-                    const double4 c = a.plane_cache[i];
-                    nx = c.x; ny = c.y; nz = c.z; d = c.w;
-                    fit = 2;
-                } else if (cached == 1) {
-                    fit = 1;
-                } else {
-                    fit = corr::fit_plane(g, key, A.prm.min_normal_norm, A.prm.plane_thickness, nx, ny, nz, d) ? 2 : 1;
+                if (nn.pos[4] >= 0 && (double)nn.d2[4] < r2max) {            // icp_test_runner.cpp:1726
+                    npt += 1;                                                 // :1731
+                    int key[5] = {nn.pos[0], nn.pos[1], nn.pos[2], nn.pos[3], nn.pos[4]};
+                    sort5(key);                                               // canonical row order, see below
+                    ok = corr::fit_plane(g, key, A.prm.min_normal_norm, A.prm.plane_thickness, nx, ny, nz, d);
                     ++n_fit;
-                    if (coherent) {
-                        if (fit == 2) a.plane_cache[i] = make_double4(nx, ny, nz, d);
-                        int* kp = a.plane_key + 5 * i;
+                }
+                if (!ok) { nx = 0.0; ny = 0.0; nz = 0.0; d = 0.0; }
+            }
+            double c[8];
+            k1::slot_front<kUseWd>(P, px, py, pz, nx, ny, nz, d, ok, c, neff);
+            __syncwarp();
+            k1::gram_accumulate_dmma(sm.tbuf[warp], lane, c, c0, c1, e0, e1);
+        }
+    } else {
+        // ---- coherent mode: 256-slot tiles, work lists per tile so that the rare searches and fits run densely
+        for (long long base = (long long)blockIdx.x * kBlock; base < A.n; base += (long long)gridDim.x * kBlock) {
+            const long long i = base + tid;
+            const bool valid = i < A.n;
+            if (tid == 0) { sm.nS = 0; sm.nF = 0; }
+            __syncthreads();
+            // -- 1. query, previous seven, certificate
+            double px = 0.0, py = 0.0, pz = 0.0;
+            bool need = false;
+            if (valid) {
+                const float4 p4 = __ldg(&A.src[i]);
+                px = (double)p4.x; py = (double)p4.y; pz = (double)p4.z;
+                // q = fl32(R p + t)  (utils.hpp:630-636)
+                const float qx = (float)(P.R[0] * px + P.R[1] * py + P.R[2] * pz + P.t[0]);
+                const float qy = (float)(P.R[3] * px + P.R[4] * py + P.R[5] * pz + P.t[1]);
+                const float qz = (float)(P.R[6] * px + P.R[7] * py + P.R[8] * pz + P.t[2]);
+                float B = a.r2_up;
+                need = true;
+                if (use_seeds) {
+                    const int4 s0 = a.nn[kNnRec * i], s1 = a.nn[kNnRec * i + 1];
+                    if (s1.z >= 0) {                                          // all seven seeds exist
+                        const int4 s2 = a.nn[kNnRec * i + 2];
+                        corr::KnnM nn;
+                        nn.pos[0] = s0.x; nn.pos[1] = s0.y; nn.pos[2] = s0.z; nn.pos[3] = s0.w;
+                        nn.pos[4] = s1.x; nn.pos[5] = s1.y; nn.pos[6] = s1.z;
 #pragma unroll
-                        for (int k = 0; k < 5; ++k) kp[k] = key[k];
+                        for (int k = 0; k < corr::kSeeds; ++k) {
+                            const float4 t = __ldg(&g.pts[nn.pos[k]]);
+                            nn.d2[k] = corr::dist2(qx, qy, qz, t);
+                            nn.idx[k] = __float_as_int(t.w);
+                        }
+                        // 16-exchange sorting network on (d2, index)
+#define DCREG_CS(x, y) cswap5(nn.d2[x], nn.idx[x], nn.pos[x], nn.d2[y], nn.idx[y], nn.pos[y])
+                        DCREG_CS(0, 6); DCREG_CS(2, 3); DCREG_CS(4, 5); DCREG_CS(0, 2); DCREG_CS(1, 4); DCREG_CS(3, 6);
+                        DCREG_CS(0, 1); DCREG_CS(2, 5); DCREG_CS(3, 4); DCREG_CS(1, 2); DCREG_CS(4, 6); DCREG_CS(2, 3);
+                        DCREG_CS(4, 5); DCREG_CS(1, 2); DCREG_CS(3, 4); DCREG_CS(5, 6);
+#undef DCREG_CS
+                        B = fminf(B, nn.d2[6] * kNnLook);
+                        const float ex = qx - __int_as_float(s2.x), ey = qy - __int_as_float(s2.y), ez = qz - __int_as_float(s2.z);
+                        const float delta = sqrtf(ex * ex + ey * ey + ez * ez);
+                        const float lb = __int_as_float(s1.w);
+                        // nothing outside the seven was closer than sqrt(lb) to q_scan; it is now at least sqrt(lb) - delta away
+                        need = !((sqrtf(nn.d2[4]) + delta) * 1.00002f + 1e-7f < sqrtf(lb) * 0.99998f);
+                        if (!need) {
+#pragma unroll
+                            for (int k = 0; k < corr::kSeeds; ++k) sm.res[tid][k] = nn.pos[k];
+                            sm.res[tid][7] = s1.w; sm.res[tid][8] = __float_as_int(nn.d2[4]); sm.res[tid][9] = 1;
+                        }
                     }
                 }
+                sm.q[tid] = make_float4(qx, qy, qz, B);
+                if (need) { sm.res[tid][9] = 2; ++n_search; }
             }
-            if (coherent) a.fit_state[i] = (signed char)fit;
-            if (nn.pos[4] >= 0 && (double)nn.d2[4] < r2max) {                // icp_test_runner.cpp:1726
-                npt += 1;                                                     // :1731
-                ok = fit == 2;
+            {   // search list of the tile (slot order)
+                const unsigned bits = __ballot_sync(0xffffffffu, need);
+                int wbase = 0;
+                if (lane == 0 && bits) wbase = atomicAdd(&sm.nS, __popc(bits));
+                wbase = __shfl_sync(0xffffffffu, wbase, 0);
+                if (need) sm.listS[wbase + __popc(bits & ((1u << lane) - 1u))] = tid;
             }
-            if (!ok) { nx = 0.0; ny = 0.0; nz = 0.0; d = 0.0; }
+            __syncthreads();
+            // -- 2. searches: few -> one warp per listed slot (the other slots' threads are not held up by a
+            //       15 us sequential search); many -> every thread searches for its own slot
+            const int nS = sm.nS;
+            if (nS <= kSearchListMax) {
+                corr::WarpKnnSmem& W = *reinterpret_cast<corr::WarpKnnSmem*>(sm.tbuf[warp]);
+                for (int w = warp; w < nS; w += kBlock / 32) {
+                    const int t = sm.listS[w];
+                    const float4 q = sm.q[t];
+                    corr::KnnM r;
+                    float lbq = a.r2_up * 0.9999f;    // nothing beyond the rings of cells is closer than the radius
+                    const bool got = corr::knn_warp_search(g, q.x, q.y, q.z, q.w, W, r, lbq);
+                    if (got) {
+                        if (lane < corr::kSeeds) sm.res[t][lane] = W.opos[lane];
+                        if (lane == 7) sm.res[t][7] = __float_as_int(lbq);
+                        if (lane == 8) sm.res[t][8] = __float_as_int(r.d2[4]);
+                        if (lane == 9) sm.res[t][9] = 0;
+                    }
+                    __syncwarp();
+                }
+                __syncthreads();
+            }
+            if (valid && sm.res[tid][9] == 2) {       // too many for the list, or more than 64 candidates inside the bound
+                const float4 q = sm.q[tid];
+                corr::KnnM r;
+                float lbq = a.r2_up * 0.9999f;
+                corr::knn_search_lb(g, q.x, q.y, q.z, q.w, r, lbq);
+#pragma unroll
+                for (int k = 0; k < corr::kSeeds; ++k) sm.res[tid][k] = r.pos[k];
+                sm.res[tid][7] = __float_as_int(lbq); sm.res[tid][8] = __float_as_int(r.d2[4]); sm.res[tid][9] = 0;
+            }
+            // -- 3a. record; which five; cached plane?
+            double nx = 0.0, ny = 0.0, nz = 0.0, d = 0.0;
+            bool ok = false, want_fit = false, have5 = false;
+            float d5 = 0.0f;
+            if (valid) {
+                int pos[corr::kSeeds];
+#pragma unroll
+                for (int k = 0; k < corr::kSeeds; ++k) pos[k] = sm.res[tid][k];
+                d5 = __int_as_float(sm.res[tid][8]);
+                a.nn[kNnRec * i] = make_int4(pos[0], pos[1], pos[2], pos[3]);
+                a.nn[kNnRec * i + 1] = make_int4(pos[4], pos[5], pos[6], sm.res[tid][7]);
+                if (sm.res[tid][9] == 0) {                                    // searched: remember where
+                    const float4 q = sm.q[tid];
+                    a.nn[kNnRec * i + 2] = make_int4(__float_as_int(q.x), __float_as_int(q.y), __float_as_int(q.z), 0);
+                }
+                have5 = pos[4] >= 0;
+                // The plane is fitted to the five points in ascending position order, not in distance order: the
+                // least-squares solution does not depend on the row order (only its last-bit rounding does), and a
+                // canonical order makes the fit a function of the SET of five, which changes far less often than
+                // their ranking.
+                int key[5] = {pos[0], pos[1], pos[2], pos[3], pos[4]};
+                sort5(key);
+                int fit = 0;                                                  // 1 = gates failed, 2 = plane valid
+                if (have5) {
+                    int cached = 0;
+                    if (use_seeds) {
+                        const int* kp = a.plane_key + 5 * i;
+                        if (kp[0] == key[0] && kp[1] == key[1] && kp[2] == key[2] && kp[3] == key[3] && kp[4] == key[4])
+                            cached = (int)a.fit_state[i];
+                    }
+                    if (cached == 2) {
+                        const double4 c = a.plane_cache[i];
+                        nx = c.x; ny = c.y; nz = c.z; d = c.w;
+                        fit = 2;
+                    } else if (cached == 1) {
+                        fit = 1;
+                    } else {
+                        want_fit = true;
+#pragma unroll
+                        for (int k = 0; k < 5; ++k) sm.key[tid][k] = key[k];
+                    }
+                }
+                if (!want_fit) { a.fit_state[i] = (signed char)fit; ok = fit == 2; }
+            }
+            {   // fit list of the tile
+                const unsigned bits = __ballot_sync(0xffffffffu, want_fit);
+                int wbase = 0;
+                if (lane == 0 && bits) wbase = atomicAdd(&sm.nF, __popc(bits));
+                wbase = __shfl_sync(0xffffffffu, wbase, 0);
+                if (want_fit) sm.listF[wbase + __popc(bits & ((1u << lane) - 1u))] = tid;
+            }
+            __syncthreads();
+            // -- 3b. fits, densely packed into the first warps
+            const int nF = sm.nF;
+            for (int f = tid; f < nF; f += kBlock) {
+                const int t = sm.listF[f];
+                int key[5];
+#pragma unroll
+                for (int k = 0; k < 5; ++k) key[k] = sm.key[t][k];
+                double fx = 0.0, fy = 0.0, fz = 0.0, fd = 0.0;
+                const int fit = corr::fit_plane(g, key, A.prm.min_normal_norm, A.prm.plane_thickness, fx, fy, fz, fd) ? 2 : 1;
+                sm.plane[t] = make_double4(fx, fy, fz, fd);
+                sm.fitres[t] = (signed char)fit;
+                const long long it = base + t;
+                if (fit == 2) a.plane_cache[it] = make_double4(fx, fy, fz, fd);
+                int* kp = a.plane_key + 5 * it;
+#pragma unroll
+                for (int k = 0; k < 5; ++k) kp[k] = key[k];
+                a.fit_state[it] = (signed char)fit;
+                ++n_fit;
+            }
+            __syncthreads();
+            // -- 3c. gate, row, Gram
+            if (valid) {
+                if (want_fit) {
+                    const double4 c = sm.plane[tid];
+                    nx = c.x; ny = c.y; nz = c.z; d = c.w;
+                    ok = sm.fitres[tid] == 2;
+                }
+                if (have5 && (double)d5 < r2max) npt += 1;                    // icp_test_runner.cpp:1726, 1731
+                else ok = false;
+                if (!ok) { nx = 0.0; ny = 0.0; nz = 0.0; d = 0.0; }
+            }
+            double c[8];
+            k1::slot_front<kUseWd>(P, px, py, pz, nx, ny, nz, d, ok, c, neff);
+            __syncwarp();
+            k1::gram_accumulate_dmma(sm.tbuf[warp], lane, c, c0, c1, e0, e1);
+            __syncthreads();
         }
-        double c[8];
-        k1::slot_front<kUseWd>(P, px, py, pz, nx, ny, nz, d, ok, c, neff);
-        __syncwarp();
-        k1::gram_accumulate_dmma(sm.tbuf[warp], lane, c, c0, c1, e0, e1);
     }
     if (a.stats) {
         n_search = __reduce_add_sync(0xffffffffu, n_search);
@@ -1047,8 +1148,16 @@ static int launch_iteration(dcreg_ctx* ctx, const dcreg_icp_params* prm, const f
         b.r2_up = r2f;
         ctx->nn_valid = true;
         const int g2 = stream_grid(ctx, ctx->n_src, 3);
-        if (prm->use_weight_derivative) icp_iter2_kernel<true><<<g2, kBlock, 0, ctx->stream>>>(b);
-        else icp_iter2_kernel<false><<<g2, kBlock, 0, ctx->stream>>>(b);
+        static bool configured = false;
+        if (!configured) {
+            CK(cudaFuncSetAttribute(icp_iter2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Iter2Smem)));
+            CK(cudaFuncSetAttribute(icp_iter2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Iter2Smem)));
+            CK(cudaFuncSetAttribute(icp_iter2_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+            CK(cudaFuncSetAttribute(icp_iter2_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+            configured = true;
+        }
+        if (prm->use_weight_derivative) icp_iter2_kernel<true><<<g2, kBlock, sizeof(Iter2Smem), ctx->stream>>>(b);
+        else icp_iter2_kernel<false><<<g2, kBlock, sizeof(Iter2Smem), ctx->stream>>>(b);
     } else {
         if (prm->use_weight_derivative) icp_iteration_kernel<true><<<grid, kBlock, 0, ctx->stream>>>(a);
         else icp_iteration_kernel<false><<<grid, kBlock, 0, ctx->stream>>>(a);
