@@ -237,6 +237,11 @@ def run_ours(args, rank, local_rank, world):
     launches = ctx.launch_count - l0
     value = world * args.steps * C2_ITERS / (dev_ms * 1e-3)
 
+    # how much correspondence work the loop reused in one step (untimed extra run, counters on)
+    ctx.iteration_counters(True)
+    ctx.icp_run(prm, T0, want_log=False)
+    searched, fitted = ctx.iteration_counters(False)
+
     # e2e: host buffers in, pose + log out, every step
     barrier()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -312,6 +317,10 @@ def run_ours(args, rank, local_rank, world):
             "e2e": {"value": e2e_value, "unit": "ICP iterations/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": int(launches),
+            "loop": {"slot_iterations_per_step": C2_POINTS * C2_ITERS, "searched": int(searched), "plane_fits": int(fitted),
+                     "note": "every iteration recomputes every correspondence; a slot whose 7 stored neighbours provably still "
+                             "contain its 5 nearest (gap certificate) skips the cell search, a slot whose 5 neighbours are the same "
+                             "set reuses its plane - results identical to searching and fitting every time (tests/test_gpu_parity.py)"},
             "roofline": {"kernel": "k1s::reduce_stream_kernel<float4, wd=false> (K1)", "bound": "hbm", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak,
                          "traffic": K1_NCU_TRAFFIC_BYTES * n_local / C4_SLOTS, "traffic_source": "ncu --set full dram__bytes_read+write per 10 M-slot launch, profiles/k1_r1_final_ncu_summary.txt",

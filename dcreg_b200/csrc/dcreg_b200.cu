@@ -457,20 +457,48 @@ __global__ void __launch_bounds__(kBlock, 3) icp_iter2_kernel(const __grid_const
 }
 
 // K2 as its own kernel (seam 3, and the sharded loop after the all-reduce).
+// K2 executes ~4 k warp instructions exactly once per launch, so it runs at instruction-fetch speed (ncu: top stall
+// no_instruction, 14 cycles per instruction).  Thanks to the programmatic dependent launch it starts while the
+// iteration kernel is still running, so it first executes the SAME code on a scratch copy of the state with the
+// previous iteration's sums (same branches, harmless stores), which pulls the instructions into the SM's caches;
+// only then does it wait for the iteration kernel and do the real step.
+static_assert(kAcc == 32, "k2_step_kernel copies acc with one element per lane");
+struct K2Scratch {
+    double acc_prev[kAcc];
+    IcpState state;
+};
+
 __global__ void __launch_bounds__(32) k2_step_kernel(const double* acc, IcpState* st, dcreg_icp_params prm,
                                                      dcreg_iter_log* log, int log_cap, const float* src_radius,
-                                                     double coherent_step) {
+                                                     double coherent_step, K2Scratch* scratch) {
     __shared__ k2::WarpSmem sm;
-    pdl_wait();                                   // acc comes from the iteration kernel (or the all-reduce) before
     pdl_release();
-    if (st->done) return;
-    // mode of the next iteration kernel: records pay off once no source point moves more than ~5 % of the search radius
-    const double lever = src_radius ? (double)*src_radius : 1.0e30;
+    const int lane = threadIdx.x;
     const double max_step = coherent_step * prm.search_radius;
-    if (prm.detection == DCREG_DET_SCHUR_CONDITION_NUMBER && prm.handling == DCREG_HAND_PRECONDITIONED_CG) {
-        k2::icp_step_warp_ours(acc, st, prm, log, log_cap, sm, lever, max_step);   // all 32 lanes cooperate
-    } else if (threadIdx.x == 0) {
-        k2::icp_step(acc, st, prm, log, log_cap, lever, max_step);    // baseline methods: generic single-thread path
+    const bool warp_path = prm.detection == DCREG_DET_SCHUR_CONDITION_NUMBER && prm.handling == DCREG_HAND_PRECONDITIONED_CG;
+#pragma unroll 1
+    for (int pass = scratch ? 0 : 1; pass < 2; ++pass) {
+        const double* acc_use = acc;
+        IcpState* st_use = st;
+        dcreg_iter_log* log_use = log;
+        if (pass == 0) {                                  // rehearsal: nothing the previous kernels still write is read
+            for (int e = lane; e < (int)(sizeof(IcpState) / sizeof(int)); e += 32)
+                reinterpret_cast<int*>(&scratch->state)[e] = reinterpret_cast<const int*>(st)[e];
+            __syncwarp();
+            acc_use = scratch->acc_prev; st_use = &scratch->state; log_use = nullptr;
+        } else {
+            pdl_wait();                                   // acc comes from the iteration kernel (or the all-reduce) before
+            if (st->done) return;
+        }
+        // mode of the next iteration kernel: records pay off once no source point moves more than ~5 % of the search radius
+        const double lever = src_radius ? (double)*src_radius : 1.0e30;
+        if (warp_path) {
+            k2::icp_step_warp_ours(acc_use, st_use, prm, log_use, log_cap, sm, lever, max_step);   // all 32 lanes cooperate
+        } else if (lane == 0) {
+            k2::icp_step(acc_use, st_use, prm, log_use, log_cap, lever, max_step);    // baseline methods: generic single-thread path
+        }
+        __syncwarp();
+        if (pass == 1 && scratch) scratch->acc_prev[lane] = acc[lane];              // kAcc == 32: next launch's rehearsal input
     }
 }
 
@@ -642,6 +670,7 @@ struct dcreg_ctx {
     IcpState* d_state = nullptr;
     dcreg_iter_log* d_log = nullptr; int log_cap = 0;
     double* d_small = nullptr;       // scratch for the seams (>= 512 doubles)
+    K2Scratch* d_k2_scratch = nullptr;   // K2's rehearsal state (see k2_step_kernel)
     dcreg_analysis* d_analysis = nullptr;
     float4* d_flush = nullptr; long long flush_n = 0;
 
@@ -864,6 +893,10 @@ int dcreg_create(int device_id, dcreg_ctx** out) {
     CK(cudaMalloc(&ctx->d_state, sizeof(IcpState)));
     CK(cudaMemsetAsync(ctx->d_state, 0, sizeof(IcpState), ctx->stream));
     CK(cudaMalloc(&ctx->d_small, 1024 * sizeof(double)));
+    if (!getenv("DCREG_NO_K2_REHEARSAL")) {
+        CK(cudaMalloc(&ctx->d_k2_scratch, sizeof(K2Scratch)));
+        CK(cudaMemsetAsync(ctx->d_k2_scratch, 0, sizeof(K2Scratch), ctx->stream));
+    }
     CK(cudaMalloc(&ctx->d_analysis, sizeof(dcreg_analysis)));
     CK(cudaStreamSynchronize(ctx->stream));
     return DCREG_OK;
@@ -877,7 +910,7 @@ int dcreg_destroy(dcreg_ctx* ctx) {
     void* ptrs[] = {ctx->d_src, ctx->d_stage, ctx->d_tgt, ctx->grid.keys, ctx->grid.cell_start, ctx->grid.hstart,
                     ctx->grid.hcount, ctx->d_src_sorted, ctx->d_cell_tmp, ctx->d_pt_cell, ctx->d_tile_sums,
                     ctx->grid.pts, ctx->d_planes64, ctx->d_planes32, ctx->d_partials, ctx->d_counter, ctx->d_acc,
-                    ctx->d_state, ctx->d_log, ctx->d_small, ctx->d_analysis, ctx->d_flush, ctx->d_nn, ctx->d_plane_cache, ctx->d_fit_state, ctx->d_iter_stats, ctx->d_src_radius, ctx->d_plane_key};
+                    ctx->d_state, ctx->d_log, ctx->d_small, ctx->d_analysis, ctx->d_flush, ctx->d_nn, ctx->d_plane_cache, ctx->d_fit_state, ctx->d_iter_stats, ctx->d_src_radius, ctx->d_plane_key, ctx->d_k2_scratch};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
@@ -1374,7 +1407,7 @@ int dcreg_time_iteration(dcreg_ctx* ctx, const dcreg_icp_params* params, const d
         if ((rc = launch_iteration(ctx, &prm, src_iter, nullptr))) return rc;
         if (what == 1) {
             if ((rc = nccl_allreduce_acc(ctx))) return rc;
-            CK(launch_pdl(k2_step_kernel, dim3(1), dim3(32), 0, ctx->stream, (const double*)ctx->d_acc, ctx->d_state, prm, (dcreg_iter_log*)nullptr, 0, (const float*)ctx->d_src_radius, coherent_step_setting()));
+            CK(launch_pdl(k2_step_kernel, dim3(1), dim3(32), 0, ctx->stream, (const double*)ctx->d_acc, ctx->d_state, prm, (dcreg_iter_log*)nullptr, 0, (const float*)ctx->d_src_radius, coherent_step_setting(), ctx->d_k2_scratch));
             ctx->launches++;
         }
     }
@@ -1449,7 +1482,7 @@ int dcreg_icp_run(dcreg_ctx* ctx, const dcreg_icp_params* params, const double T
         for (int k = 0; k < todo; ++k) {
             if ((rc = launch_iteration(ctx, params, src_iter, nullptr))) return rc;
             if ((rc = nccl_allreduce_acc(ctx))) return rc;          // no-op on one GPU
-            CK(launch_pdl(k2_step_kernel, dim3(1), dim3(32), 0, ctx->stream, (const double*)ctx->d_acc, ctx->d_state, *params, dlog, log_cap, (const float*)ctx->d_src_radius, coherent_step_setting()));
+            CK(launch_pdl(k2_step_kernel, dim3(1), dim3(32), 0, ctx->stream, (const double*)ctx->d_acc, ctx->d_state, *params, dlog, log_cap, (const float*)ctx->d_src_radius, coherent_step_setting(), ctx->d_k2_scratch));
             ctx->launches++;
         }
         issued += todo;
@@ -1500,7 +1533,7 @@ int dcreg_icp_run_host_planes(dcreg_ctx* ctx, const dcreg_icp_params* params, co
         if ((rc = launch_reduce(ctx, ctx->d_src, ctx->d_planes64, true, ctx->n_src, &P, params->use_weight_derivative)))
             return rc;
         if ((rc = nccl_allreduce_acc(ctx))) return rc;
-        CK(launch_pdl(k2_step_kernel, dim3(1), dim3(32), 0, ctx->stream, (const double*)ctx->d_acc, ctx->d_state, *params, dlog, log_cap, (const float*)ctx->d_src_radius, coherent_step_setting()));
+        CK(launch_pdl(k2_step_kernel, dim3(1), dim3(32), 0, ctx->stream, (const double*)ctx->d_acc, ctx->d_state, *params, dlog, log_cap, (const float*)ctx->d_src_radius, coherent_step_setting(), ctx->d_k2_scratch));
         ctx->launches++;
         CK(cudaMemcpyAsync(hs, ctx->d_state, sizeof(IcpState), cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));

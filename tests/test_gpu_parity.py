@@ -5,6 +5,7 @@ Tolerances (north_star): pose 1e-6 on the SE(3) log, Schur eigenvalues 1e-8 rela
 different order).  Integer outputs (counts, masks, iteration counts) must be identical.
 """
 import math
+import os
 
 import numpy as np
 import pytest
@@ -350,6 +351,47 @@ def test_icp_fixed_iterations_synthetic_cylinder(ctx):
     res = ctx.icp_run(gpu_params(prm, fixed_iterations=1), T0)
     assert res.iterations == 12 and not res.converged
     check_against_oracle(res, conv, T, logs, status)
+
+
+@pytest.mark.parametrize("method", ["Ours", "ME-TSVD"])
+def test_loop_with_reused_correspondences_equals_full_search_every_iteration(ctx, method):
+    """The loop's iteration kernel reuses neighbour lists (gap certificate) and plane fits (same five points) once the
+    pose moves little.  Against the same loop with a full search and a fresh fit in EVERY iteration (the one-thread-per-
+    slot kernel, DCREG_FUSED_SEARCH=1) the per-iteration counts must be identical and the poses equal to rounding; the
+    counters show that the reuse paths were actually taken."""
+    from dcreg_b200 import default_params
+    from dcreg_b200.scenes import make_cylinder
+    pts = make_cylinder(30_000, seed=7)
+    T0 = o.pose6d_to_matrix(0.1, 0.3, 0.2, math.radians(0.1), math.radians(-0.1), math.radians(1.0))
+    det, hand = METHODS[method]
+    prm = default_params(max_iterations=40, fixed_iterations=1, kappa_target=10.0, detection=det, handling=hand)
+    ctx.set_source(pts); ctx.set_target(pts, 1.0)
+    ctx.iteration_counters(True)
+    res = ctx.icp_run(prm, T0)
+    searched, fitted = ctx.iteration_counters(False)
+    os.environ["DCREG_FUSED_SEARCH"] = "1"
+    try:
+        ref = ctx.icp_run(prm, T0)
+    finally:
+        del os.environ["DCREG_FUSED_SEARCH"]
+    assert res.iterations == ref.iterations == 40
+    for A, B in zip(res.logs, ref.logs):
+        assert A.n_effective == B.n_effective and A.n_corr_pt == B.n_corr_pt
+        assert o.se3_log_distance(np.array(A.T).reshape(4, 4), np.array(B.T).reshape(4, 4)) < 1e-11
+        assert abs(A.rmse - B.rmse) < 1e-12
+    # 40 iterations x 30k slots = 1.2 M slot-iterations: well under half of them searched / fitted
+    assert 30_000 <= searched < 600_000 and 30_000 <= fitted < 600_000
+
+
+def test_iteration_timing_entry_point(ctx):
+    from dcreg_b200 import default_params
+    from dcreg_b200.scenes import make_cylinder
+    pts = make_cylinder(20_000, seed=3)
+    ctx.set_source(pts); ctx.set_target(pts, 1.0)
+    prm = default_params(kappa_target=10.0)
+    T0 = o.pose6d_to_matrix(0.05, 0.05, 0.05, 0.0, 0.0, math.radians(0.5))
+    assert 0.0 < ctx.time_iteration(prm, T0, 0, 5) < 5.0
+    assert 0.0 < ctx.time_iteration(prm, T0, 1, 5) < 5.0
 
 
 def test_icp_corridor_weakest_translation_is_the_axis(ctx):
