@@ -38,7 +38,7 @@ C2_ITERS = 50
 C4_SLOTS = 10_000_000
 C4_RADIUS = 0.05
 ALG_BYTES_PER_SLOT = 32          # float4 point + float4 plane
-K1_NCU_TRAFFIC_BYTES = 320.06e6 + 3.56e6   # dram read + write of one 10 M-slot K1 launch (ncu, profiles/)
+K1_NCU_TRAFFIC_BYTES = 320.06e6 + 3.93e6   # dram read + write of one 10 M-slot K1 launch (ncu --set full, profiles/k1_r1_final_ncu_summary.txt)
 
 
 def env_int(name, default):
