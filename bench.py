@@ -320,7 +320,7 @@ def run_ours(args, rank, local_rank, world):
             "loop": {"slot_iterations_per_step": C2_POINTS * C2_ITERS, "searched": int(searched), "plane_fits": int(fitted),
                      "note": "every iteration recomputes every correspondence; a slot whose 7 stored neighbours provably still "
                              "contain its 5 nearest (gap certificate) skips the cell search, a slot whose 5 neighbours are the same "
-                             "set reuses its plane - results identical to searching and fitting every time (tests/test_gpu_parity.py)"},
+                             "ordered list reuses its plane - results identical to searching and fitting every time (tests/test_gpu_parity.py)"},
             "roofline": {"kernel": "k1s::reduce_stream_kernel<float4, wd=false> (K1)", "bound": "hbm", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak,
                          "traffic": K1_NCU_TRAFFIC_BYTES * n_local / C4_SLOTS, "traffic_source": "ncu --set full dram__bytes_read+write per 10 M-slot launch, profiles/k1_r1_final_ncu_summary.txt",

@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(kBlock, 3) icp_iteration_kernel(const __grid_c
 //      the 8th candidate is far), or the search radius on the first iteration.
 //   4. neighbour record to HBM (next iteration's seeds); plane fit to the first five, reused while the ordered
 //      list of five stays the same (same five rows in the same order give the same QR bit for bit); residual /
-//      weight / Jacobian row; DMMA Gram accumulation.
+//      weight / Jacobian row; DMMA Gram accumulation.  Searches and fits of a 256-slot tile go through work lists.
 // Tail: packed per-block partial, atomic ticket, last block reduces (k1s::finish_packed).
 // Record per slot (3 int4): {pos0..pos3}, {pos4..pos6, bits(lb8)}, {bits(q_scan.xyz), flags};
 // pos = position in the grid's point array (ascending (d2, index) at the time of writing), -1 = none.
@@ -157,7 +157,7 @@ struct Iter2Smem {
     // coherent mode, per 256-slot tile
     float4 q[kBlock];                           // query (x, y, z), w = search bound B
     int res[kBlock][10];                        // pos0..pos6, bits(lb), bits(d2 of the 5th), 1 = no search / 0 = searched / 2 = search pending
-    int key[kBlock][5];                         // the five positions, ascending (slots that need a fit)
+    int key[kBlock][5];                         // the five positions in distance order (slots that need a fit)
     double4 plane[kBlock];
     signed char fitres[kBlock];
     int listS[kBlock], listF[kBlock];
@@ -169,7 +169,7 @@ struct Iter2Args {
     int4* nn;                 // [kNnRec n] neighbour records
     double4* plane_cache;     // plane fitted to the slot's current five neighbours (reused while the set stays)
     signed char* fit_state;   // 0 = nothing cached, 1 = cached fit failed its gates, 2 = cached plane valid
-    int* plane_key;           // [5 n] the five positions (ascending) the cached plane was fitted to
+    int* plane_key;           // [5 n] the five positions (in distance order) the cached plane was fitted to
     int coop_max;             // (unused by the tiled path) kept for profiling builds
     int force;                // 0: mode and seeds from the loop state (written by K2); 1: coherent mode, seeds = use_seeds
     int use_seeds;            // (force) records of the previous launch are valid
@@ -183,13 +183,6 @@ __device__ __forceinline__ void cswap5(float& da, int& ia, int& pa, float& db, i
         const int ti = ia; ia = ib; ib = ti;
         const int tp = pa; pa = pb; pb = tp;
     }
-}
-
-__device__ __forceinline__ void sort5(int (&key)[5]) {
-#define DCREG_CI(x, y) { const int lo = min(key[x], key[y]), hi = max(key[x], key[y]); key[x] = lo; key[y] = hi; }
-    DCREG_CI(0, 1); DCREG_CI(3, 4); DCREG_CI(2, 4); DCREG_CI(2, 3); DCREG_CI(0, 3); DCREG_CI(0, 2);
-    DCREG_CI(1, 4); DCREG_CI(1, 3); DCREG_CI(1, 2);
-#undef DCREG_CI
 }
 
 template <bool kUseWd>
@@ -231,9 +224,7 @@ __global__ void __launch_bounds__(kBlock, 3) icp_iter2_kernel(const __grid_const
                 ++n_search;
                 if (nn.pos[4] >= 0 && (double)nn.d2[4] < r2max) {            // icp_test_runner.cpp:1726
                     npt += 1;                                                 // :1731
-                    int key[5] = {nn.pos[0], nn.pos[1], nn.pos[2], nn.pos[3], nn.pos[4]};
-                    sort5(key);                                               // canonical row order, see below
-                    ok = corr::fit_plane(g, key, A.prm.min_normal_norm, A.prm.plane_thickness, nx, ny, nz, d);
+                    ok = corr::fit_plane(g, nn.pos, A.prm.min_normal_norm, A.prm.plane_thickness, nx, ny, nz, d);
                     ++n_fit;
                 }
                 if (!ok) { nx = 0.0; ny = 0.0; nz = 0.0; d = 0.0; }
@@ -351,12 +342,10 @@ __global__ void __launch_bounds__(kBlock, 3) icp_iter2_kernel(const __grid_const
                     a.nn[kNnRec * i + 2] = make_int4(__float_as_int(q.x), __float_as_int(q.y), __float_as_int(q.z), 0);
                 }
                 have5 = pos[4] >= 0;
-                // The plane is fitted to the five points in ascending position order, not in distance order: the
-                // least-squares solution does not depend on the row order (only its last-bit rounding does), and a
-                // canonical order makes the fit a function of the SET of five, which changes far less often than
-                // their ranking.
-                int key[5] = {pos[0], pos[1], pos[2], pos[3], pos[4]};
-                sort5(key);
+                // The plane is a function of the five target points IN THEIR ORDER (the rows of the 5x3 system keep the
+                // reference's distance order, so the QR rounds exactly as a fresh fit would): the cache key is the
+                // ordered list.  A pure re-ranking therefore refits; the fit list keeps that cheap.
+                const int key[5] = {pos[0], pos[1], pos[2], pos[3], pos[4]};
                 int fit = 0;                                                  // 1 = gates failed, 2 = plane valid
                 if (have5) {
                     int cached = 0;

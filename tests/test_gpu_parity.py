@@ -383,6 +383,39 @@ def test_loop_with_reused_correspondences_equals_full_search_every_iteration(ctx
     assert 30_000 <= searched < 600_000 and 30_000 <= fitted < 600_000
 
 
+def test_loop_reuse_on_a_lattice_with_duplicates_and_ties(ctx):
+    """Worst case for the neighbour bookkeeping: a regular lattice (many exactly equal distances -> index rule),
+    duplicated target points, a dense patch (more than 64 candidates inside a loose bound -> the warp search gives up
+    and the slot searches sequentially) and a source that is not a multiple of the tile size."""
+    from dcreg_b200 import default_params
+    g = np.arange(-6, 6, 0.25, dtype=np.float32)
+    X, Y = np.meshgrid(g, g)
+    floor = np.stack([X.ravel(), Y.ravel(), np.zeros(X.size, np.float32)], axis=1)
+    wall = np.stack([X.ravel(), np.full(X.size, 6.0, np.float32), (Y.ravel() + 6.0) * 0.5], axis=1)
+    wall2 = np.stack([np.full(X.size, -6.0, np.float32), X.ravel(), (Y.ravel() + 6.0) * 0.5], axis=1)
+    d = np.arange(-1, 1, 0.05, dtype=np.float32)
+    DX, DY = np.meshgrid(d, d)
+    dense = np.stack([DX.ravel(), DY.ravel(), np.zeros(DX.size, np.float32)], axis=1)
+    tgt = np.concatenate([floor, wall, wall2, dense, floor[::5]]).astype(np.float32)       # floor[::5]: exact duplicates
+    rng = np.random.default_rng(5)
+    src = tgt[rng.permutation(len(tgt))[:7001]].copy()
+    T0 = o.pose6d_to_matrix(0.06, -0.05, 0.04, math.radians(0.2), math.radians(-0.1), math.radians(0.4))
+    prm = default_params(max_iterations=25, fixed_iterations=1, kappa_target=10.0)
+    ctx.set_source(src); ctx.set_target(tgt, 1.0)
+    res = ctx.icp_run(prm, T0)
+    os.environ["DCREG_FUSED_SEARCH"] = "1"
+    try:
+        ref = ctx.icp_run(prm, T0)
+    finally:
+        del os.environ["DCREG_FUSED_SEARCH"]
+    assert res.status == ref.status and res.iterations == ref.iterations
+    for A, B in zip(res.logs, ref.logs):
+        assert A.n_effective == B.n_effective and A.n_corr_pt == B.n_corr_pt
+        # same correspondences, same planes; the 27 sums are added in a different order and this lattice scene is
+        # ill-conditioned (many rank-deficient neighbourhoods), so the poses agree to ~1e-10 rather than 1e-12
+        assert o.se3_log_distance(np.array(A.T).reshape(4, 4), np.array(B.T).reshape(4, 4)) < 1e-8
+
+
 def test_iteration_timing_entry_point(ctx):
     from dcreg_b200 import default_params
     from dcreg_b200.scenes import make_cylinder

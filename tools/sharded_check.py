@@ -14,7 +14,7 @@ torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 pts = make_cylinder(60_000, seed=42)
 T0 = g2_initial_pose()
-prm = default_params(max_iterations=8, fixed_iterations=1, kappa_target=10.0)
+prm = default_params(max_iterations=30, fixed_iterations=1, kappa_target=10.0)   # long enough to reach the record-reusing mode
 ctx = Context(local)
 ctx.set_target(pts, 1.0)
 # single-GPU reference on every rank
