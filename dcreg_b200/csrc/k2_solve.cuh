@@ -355,7 +355,9 @@ __device__ __noinline__ void boxplus(double* R, double* t, const double* dx) {
         const double K[9] = {0.0, -az, ay, az, 0.0, -ax, -ay, ax, 0.0};
         double K2[9];
         dla::mat3_mul(K, K, K2);
-        const double s = sin(theta), c1 = 1.0 - cos(theta);
+        double s, c;
+        sincos(theta, &s, &c);
+        const double c1 = 1.0 - c;
         for (int i = 0; i < 9; ++i) E[i] = ((i % 4 == 0) ? 1.0 : 0.0) + s * K[i] + c1 * K2[i];
     }
     double Rn[9];
@@ -451,22 +453,26 @@ struct WarpSmem {
     double lam[2][3], V[2][9];
     double P[36];
     double dx[6];
+    double Rt[12];           // pose copy: boxplus works on shared memory, lanes write it back in parallel
+    double ilam[2][3];       // 1 / clamped Schur eigenvalues (preconditioner)
     int ok[2];
 };
 
+// The PCG runs on lanes 0..7 only (components live in lanes 0..5): 3 shuffle rounds per dot product instead of 5.
+constexpr unsigned kPcgMask = 0xffu;
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    for (int off = 4; off > 0; off >>= 1) v += __shfl_xor_sync(kPcgMask, v, off);
     return v;
 }
 __device__ __forceinline__ double row_dot_bcast(const double (&row)[6], double v) {   // sum_j row[j] * v(lane j)
     double s = 0.0;
 #pragma unroll
-    for (int j = 0; j < 6; ++j) s = fma(row[j], __shfl_sync(0xffffffffu, v, j), s);
+    for (int j = 0; j < 6; ++j) s = fma(row[j], __shfl_sync(kPcgMask, v, j), s);
     return s;
 }
 
-// PCG on H x = g (paper Alg. 3): lanes 0..5 own rows/components, all 32 lanes execute.  Returns iterations used.
+// PCG on H x = g (paper Alg. 3): lanes 0..5 own rows/components, lanes 0..7 execute.  Returns iterations used.
 __device__ __forceinline__ int pcg6_warp(const WarpSmem& sm, int lane, int max_iter, double tol, double& x_out) {
     double Hrow[6], Prow[6];
 #pragma unroll
@@ -505,6 +511,7 @@ __device__ inline void icp_step_warp_ours(const double* acc, IcpState* st, const
         sm.H[e] = acc[a * 6 - (a * (a - 1)) / 2 + (b - a)];
     }
     if (lane < 6) sm.g[lane] = acc[21 + lane];
+    if (lane >= 8 && lane < 20) sm.Rt[lane - 8] = lane < 17 ? st->R[lane - 8] : st->t[lane - 17];
     if (rec) {
         if (lane < 27) rec->H27[lane] = acc[lane];
         if (lane == 0) { rec->iter = iter; rec->n_effective = n_eff; rec->n_corr_pt = n_pt; rec->status = DCREG_OK; }
@@ -572,14 +579,20 @@ __device__ inline void icp_step_warp_ours(const double* acc, IcpState* st, const
             deg = l[2] / fmax(l[lane % 3], 1e-12) > prm.cond_thresh;
         }
         degenerate = __ballot_sync(0xffffffffu, deg) != 0u;
+        if (lane < 6) {
+            const double* l = sm.lam[lane / 3];
+            sm.ilam[lane / 3][lane % 3] = 1.0 / fmax(l[lane % 3], l[2] / prm.kappa_target);
+        }
+        __syncwarp();
         for (int e = lane; e < 36; e += 32) {
             const int i = e / 6, j = e % 6;
             double v = 0.0;
             if (i / 3 == j / 3) {
                 const int blk = i / 3;
-                const double* l = sm.lam[blk];
+                const double* il = sm.ilam[blk];
                 const double* Vb = sm.V[blk];
-                for (int k = 0; k < 3; ++k) v += Vb[(i % 3) * 3 + k] * Vb[(j % 3) * 3 + k] / fmax(l[k], l[2] / prm.kappa_target);
+#pragma unroll
+                for (int k = 0; k < 3; ++k) v = fma(Vb[(i % 3) * 3 + k] * Vb[(j % 3) * 3 + k], il[k], v);
             }
             sm.P[e] = v;
         }
@@ -587,9 +600,11 @@ __device__ inline void icp_step_warp_ours(const double* acc, IcpState* st, const
     }
     // ---- solve ----
     if (degenerate) {
-        double xi;
-        pcg6_warp(sm, lane, prm.pcg_max_iter, prm.pcg_tol, xi);
-        if (lane < 6) sm.dx[lane] = xi;
+        if (lane < 8) {
+            double xi;
+            pcg6_warp(sm, lane, prm.pcg_max_iter, prm.pcg_tol, xi);
+            if (lane < 6) sm.dx[lane] = xi;
+        }
     } else if (lane == 0) {
         qr6(sm.H, sm.g, sm.dx);                              // dcreg.hpp:190
     }
@@ -609,7 +624,7 @@ __device__ inline void icp_step_warp_ours(const double* acc, IcpState* st, const
     }
     for (int e = lane; e < 36; e += 32) st->H_last[e] = sm.H[e];     // matAtA_last, icp_test_runner.cpp:1965
     if (lane == 0) {
-        boxplus(st->R, st->t, sm.dx);                        // icp_test_runner.cpp:1953
+        boxplus(sm.Rt, sm.Rt + 9, sm.dx);                    // icp_test_runner.cpp:1953
         note_step(st, sm.dx, lever, max_step);
         const double dR = sqrt(sm.dx[0] * sm.dx[0] + sm.dx[1] * sm.dx[1] + sm.dx[2] * sm.dx[2]);
         const double dT = sqrt(sm.dx[3] * sm.dx[3] + sm.dx[4] * sm.dx[4] + sm.dx[5] * sm.dx[5]);
@@ -621,11 +636,13 @@ __device__ inline void icp_step_warp_ours(const double* acc, IcpState* st, const
         }
     }
     __syncwarp();
+    if (lane < 9) st->R[lane] = sm.Rt[lane];
+    else if (lane < 12) st->t[lane - 9] = sm.Rt[lane];
     if (rec) {
         if (lane < 6) rec->dx[lane] = sm.dx[lane];
         if (lane < 16) {
             const int r = lane / 4, c = lane % 4;
-            rec->T[lane] = r == 3 ? (c == 3 ? 1.0 : 0.0) : (c == 3 ? st->t[r] : st->R[r * 3 + c]);
+            rec->T[lane] = r == 3 ? (c == 3 ? 1.0 : 0.0) : (c == 3 ? sm.Rt[9 + r] : sm.Rt[r * 3 + c]);
         }
     }
 }

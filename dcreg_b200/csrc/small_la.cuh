@@ -106,7 +106,7 @@ __device__ __noinline__ void jacobi_eigh3(const double* Ain, double* w, double* 
                 const double app = a[p][p], aqq = a[q][q];
                 const double theta = (aqq - app) / (2.0 * apq);
                 const double tt = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
-                const double c = 1.0 / sqrt(tt * tt + 1.0), sn = tt * c;
+                const double c = rsqrt(tt * tt + 1.0), sn = tt * c;
                 const double tau = sn / (1.0 + c);
                 a[p][p] = app - tt * apq;
                 a[q][q] = aqq + tt * apq;
@@ -282,7 +282,9 @@ __device__ __noinline__ bool fullpiv_inverse(double* A, double* Ainv) {
     const double thr = 2.220446049250313e-16 * (double)N * maxpivot;
     for (int k = 0; k < N; ++k)
         if (fabs(A[k * N + k]) <= thr) return false;
-    // Solve P A Q = L U  =>  A^-1 = Q U^-1 L^-1 P.  Column by column.
+    // Solve P A Q = L U  =>  A^-1 = Q U^-1 L^-1 P.  Column by column (N reciprocals instead of N^2 divisions).
+    double rd[N];
+    for (int i = 0; i < N; ++i) rd[i] = 1.0 / A[i * N + i];
     for (int col = 0; col < N; ++col) {
         double y[N];
         // rhs = P e_col : apply the row swaps in order to the unit vector
@@ -293,7 +295,7 @@ __device__ __noinline__ bool fullpiv_inverse(double* A, double* Ainv) {
             for (int j = 0; j < i; ++j) y[i] -= A[i * N + j] * y[j];
         for (int i = N - 1; i >= 0; --i) {
             for (int j = i + 1; j < N; ++j) y[i] -= A[i * N + j] * y[j];
-            y[i] /= A[i * N + i];
+            y[i] *= rd[i];
         }
         // undo the column swaps (reverse order)
         for (int k = N - 1; k >= 0; --k)
