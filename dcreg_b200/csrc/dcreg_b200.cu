@@ -147,7 +147,6 @@ __global__ void __launch_bounds__(kBlock, 3) icp_iteration_kernel(const __grid_c
 constexpr int kNnRec = 3;
 constexpr float kNnLook = 1.21f;              // squared-distance look-ahead beyond the seed bound (any value >= 1 is exact)
 constexpr double kCoherentStep = 0.05;        // records are used once no source point moves more than this x search radius per iteration
-constexpr int kCoopMax = 12;                  // up to this many searching slots per warp are searched by the whole warp
 
 constexpr int kSearchListMax = 96;            // more searching slots than this in a 256-slot tile: every thread searches for itself
 
@@ -170,7 +169,7 @@ struct Iter2Args {
     double4* plane_cache;     // plane fitted to the slot's current five neighbours (reused while the set stays)
     signed char* fit_state;   // 0 = nothing cached, 1 = cached fit failed its gates, 2 = cached plane valid
     int* plane_key;           // [5 n] the five positions (in distance order) the cached plane was fitted to
-    int coop_max;             // (unused by the tiled path) kept for profiling builds
+    int coop_max;             // more searching slots than this in a tile: every thread searches for itself (kSearchListMax)
     int force;                // 0: mode and seeds from the loop state (written by K2); 1: coherent mode, seeds = use_seeds
     int use_seeds;            // (force) records of the previous launch are valid
     float r2_up;              // search radius^2 rounded up to float
@@ -299,7 +298,7 @@ __global__ void __launch_bounds__(kBlock, 3) icp_iter2_kernel(const __grid_const
             // -- 2. searches: few -> one warp per listed slot (the other slots' threads are not held up by a
             //       15 us sequential search); many -> every thread searches for its own slot
             const int nS = sm.nS;
-            if (nS <= kSearchListMax) {
+            if (nS <= a.coop_max) {
                 corr::WarpKnnSmem& W = *reinterpret_cast<corr::WarpKnnSmem*>(sm.tbuf[warp]);
                 for (int w = warp; w < nS; w += kBlock / 32) {
                     const int t = sm.listS[w];
@@ -1186,7 +1185,7 @@ static int launch_iteration(dcreg_ctx* ctx, const dcreg_icp_params* prm, const f
         b.it = a;
         b.nn = ctx->d_nn; b.plane_cache = ctx->d_plane_cache; b.fit_state = ctx->d_fit_state; b.plane_key = ctx->d_plane_key;
         b.force = ctx->force_coherent ? 1 : 0;
-        { static int cm = -1; if (cm < 0) { const char* e = getenv("DCREG_COOP_MAX"); cm = e ? atoi(e) : kCoopMax; } b.coop_max = cm; }
+        { static int cm = -1; if (cm < 0) { const char* e = getenv("DCREG_COOP_MAX"); cm = e ? atoi(e) : kSearchListMax; } b.coop_max = cm; }
         b.use_seeds = ctx->nn_valid ? 1 : 0;
         b.stats = ctx->d_iter_stats;
         const double r2 = prm->search_radius * prm->search_radius;
