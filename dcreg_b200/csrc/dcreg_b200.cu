@@ -173,6 +173,7 @@ struct Iter2Args {
     int force;                // 0: mode and seeds from the loop state (written by K2); 1: coherent mode, seeds = use_seeds
     int use_seeds;            // (force) records of the previous launch are valid
     float r2_up;              // search radius^2 rounded up to float
+    float look;               // squared-distance look-ahead beyond the seed bound (kNnLook)
     unsigned int* stats;      // optional [2]: slots that searched, slots that refitted (profiling)
 };
 
@@ -271,7 +272,7 @@ __global__ void __launch_bounds__(kBlock, 3) icp_iter2_kernel(const __grid_const
                         DCREG_CS(0, 1); DCREG_CS(2, 5); DCREG_CS(3, 4); DCREG_CS(1, 2); DCREG_CS(4, 6); DCREG_CS(2, 3);
                         DCREG_CS(4, 5); DCREG_CS(1, 2); DCREG_CS(3, 4); DCREG_CS(5, 6);
 #undef DCREG_CS
-                        B = fminf(B, nn.d2[6] * kNnLook);
+                        B = fminf(B, nn.d2[6] * a.look);
                         const float ex = qx - __int_as_float(s2.x), ey = qy - __int_as_float(s2.y), ez = qz - __int_as_float(s2.z);
                         const float delta = sqrtf(ex * ex + ey * ey + ez * ez);
                         const float lb = __int_as_float(s1.w);
@@ -1187,6 +1188,7 @@ static int launch_iteration(dcreg_ctx* ctx, const dcreg_icp_params* prm, const f
         b.force = ctx->force_coherent ? 1 : 0;
         { static int cm = -1; if (cm < 0) { const char* e = getenv("DCREG_COOP_MAX"); cm = e ? atoi(e) : kSearchListMax; } b.coop_max = cm; }
         b.use_seeds = ctx->nn_valid ? 1 : 0;
+        { static float lk = -1.f; if (lk < 0.f) { const char* e = getenv("DCREG_LOOK"); lk = e ? (float)atof(e) : kNnLook; } b.look = lk; }
         b.stats = ctx->d_iter_stats;
         const double r2 = prm->search_radius * prm->search_radius;
         float r2f = (float)r2;
