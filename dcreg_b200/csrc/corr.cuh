@@ -707,4 +707,33 @@ __device__ __forceinline__ bool fit_plane(const Grid& g, const int (&kpos)[5], d
     return worst < thickness * thickness;                // :1772-1773
 }
 
+// The same fit with the register-resident QR (small_la.cuh: same operations in the same order).  A separate function
+// with its own register allocation: it is called from the fit work list of the loop kernel, where almost nothing is
+// live across the call (inlined into a loop body full of live state it spills; measured 3.7x slower there).
+__device__ __noinline__ bool fit_plane_reg(const Grid& g, const int (&kpos)[5], double min_norm, double thickness,
+                                           double& nx, double& ny, double& nz, double& d) {
+    double A[5][3], b[5], x[3];
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+        const float4 p = __ldg(&g.pts[kpos[j]]);
+        A[j][0] = (double)p.x;
+        A[j][1] = (double)p.y;
+        A[j][2] = (double)p.z;
+        b[j] = -1.0;
+    }
+    dla::colpiv_qr_solve_reg<5, 3>(A, b, x);
+    const double ps = sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
+    if (!(ps >= min_norm)) return false;                 // :1752 (also rejects NaN)
+    nx = x[0] / ps; ny = x[1] / ps; nz = x[2] / ps; d = 1.0 / ps;
+    double worst = 0.0;
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+        const float4 p = __ldg(&g.pts[kpos[j]]);
+        double e = nx * (double)p.x + ny * (double)p.y + nz * (double)p.z + d;
+        e *= e;
+        worst = fmax(worst, e);
+    }
+    return worst < thickness * thickness;                // :1772-1773
+}
+
 }  // namespace corr

@@ -384,7 +384,7 @@ __global__ void __launch_bounds__(kBlock, 3) icp_iter2_kernel(const __grid_const
 #pragma unroll
                 for (int k = 0; k < 5; ++k) key[k] = sm.key[t][k];
                 double fx = 0.0, fy = 0.0, fz = 0.0, fd = 0.0;
-                const int fit = corr::fit_plane(g, key, A.prm.min_normal_norm, A.prm.plane_thickness, fx, fy, fz, fd) ? 2 : 1;
+                const int fit = corr::fit_plane_reg(g, key, A.prm.min_normal_norm, A.prm.plane_thickness, fx, fy, fz, fd) ? 2 : 1;
                 sm.plane[t] = make_double4(fx, fy, fz, fd);
                 sm.fitres[t] = (signed char)fit;
                 const long long it = base + t;

@@ -104,8 +104,10 @@ __device__ __noinline__ void jacobi_eigh3(const double* Ain, double* w, double* 
                 const double apq = a[p][q];
                 if (fabs(apq) < 1e-300) { a[p][q] = a[q][p] = 0.0; continue; }
                 const double app = a[p][p], aqq = a[q][q];
-                const double theta = (aqq - app) / (2.0 * apq);
-                const double tt = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                // t = sgn(theta) / (|theta| + sqrt(theta^2 + 1)) with theta = d / h, written without forming theta:
+                // one division and one square root instead of two divisions and a square root
+                const double d = aqq - app, h = 2.0 * apq;
+                const double tt = copysign(fabs(h), d * h >= 0.0 ? 1.0 : -1.0) / (fabs(d) + sqrt(d * d + h * h));
                 const double c = rsqrt(tt * tt + 1.0), sn = tt * c;
                 const double tau = sn / (1.0 + c);
                 a[p][p] = app - tt * apq;
@@ -153,7 +155,7 @@ __device__ __noinline__ void jacobi_eigh3(const double* Ain, double* w, double* 
 // H.colPivHouseholderQr().solve(g) (dcreg.hpp:182,190,197).
 // ---------------------------------------------------------------------------------------------
 template <int M, int N>
-__device__ __noinline__ void colpiv_qr_solve(double* A, double* b, double* x) {
+__host__ __device__ __noinline__ void colpiv_qr_solve(double* A, double* b, double* x) {
     const double eps = 2.220446049250313e-16;
     double normU[N], normD[N];
     int perm[N];
@@ -243,6 +245,128 @@ __device__ __noinline__ void colpiv_qr_solve(double* A, double* b, double* x) {
 #pragma unroll
     for (int i = 0; i < N; ++i) x[i] = 0.0;
     for (int i = 0; i < nz; ++i) x[perm[i]] = c[i];
+}
+
+// Same algorithm, same operations in the same order (bit-identical results, tools/test_qr_reg.cu), but every array
+// index is a compile-time constant after unrolling: the pivot column is brought to position k with conditional
+// swaps against each later column and the rank cut `nz` becomes a predicate, so A, b and the norms stay in registers
+// instead of local memory.  Used for the 5x3 plane fit, which runs once per source slot.
+template <int M, int N>
+__host__ __device__ __forceinline__ void colpiv_qr_solve_reg(double (&A)[M][N], double (&b)[M], double (&x)[N]) {
+    const double eps = 2.220446049250313e-16;
+    double normU[N], normD[N];
+    int perm[N];
+    double maxn = 0.0;
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+        double s = 0.0;
+#pragma unroll
+        for (int i = 0; i < M; ++i) s += A[i][j] * A[i][j];
+        normU[j] = normD[j] = sqrt(s);
+        perm[j] = j;
+        if (normU[j] > maxn) maxn = normU[j];
+    }
+    const double thr_helper = (maxn * eps) * (maxn * eps) / (double)M;
+    const double downdate_thr = 1.4901161193847656e-08;  // sqrt(eps)
+    int nz = N;
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        int big = k;
+        double bign = normU[k];
+#pragma unroll
+        for (int j = k + 1; j < N; ++j)
+            if (normU[j] > bign) { bign = normU[j]; big = j; }
+        if (nz == N && bign * bign < thr_helper * (double)(M - k)) nz = k;
+#pragma unroll
+        for (int j = k + 1; j < N; ++j) {
+            if (big == j) {
+#pragma unroll
+                for (int i = 0; i < M; ++i) { const double tmp = A[i][k]; A[i][k] = A[i][j]; A[i][j] = tmp; }
+                double tn = normU[k]; normU[k] = normU[j]; normU[j] = tn;
+                tn = normD[k]; normD[k] = normD[j]; normD[j] = tn;
+                const int tp = perm[k]; perm[k] = perm[j]; perm[j] = tp;
+            }
+        }
+        // Householder reflector for column k, rows k..M-1:  H = I - tau v v^T, v = (1, ess)
+        double tail = 0.0;
+#pragma unroll
+        for (int i = k + 1; i < M; ++i) tail += A[i][k] * A[i][k];
+        const double c0 = A[k][k];
+        double tau, beta;
+        if (tail <= 2.2250738585072014e-308) {
+            tau = 0.0; beta = c0;
+#pragma unroll
+            for (int i = k + 1; i < M; ++i) A[i][k] = 0.0;
+        } else {
+            beta = sqrt(c0 * c0 + tail);
+            if (c0 >= 0.0) beta = -beta;
+            const double inv = 1.0 / (c0 - beta);
+#pragma unroll
+            for (int i = k + 1; i < M; ++i) A[i][k] *= inv;
+            tau = (beta - c0) / beta;
+        }
+        A[k][k] = beta;
+        // apply to the remaining columns and to b
+#pragma unroll
+        for (int j = k + 1; j < N; ++j) {
+            double tmp = A[k][j];
+#pragma unroll
+            for (int i = k + 1; i < M; ++i) tmp += A[i][k] * A[i][j];
+            A[k][j] -= tau * tmp;
+#pragma unroll
+            for (int i = k + 1; i < M; ++i) A[i][j] -= tau * A[i][k] * tmp;
+        }
+        if (k < nz) {
+            double tmp = b[k];
+#pragma unroll
+            for (int i = k + 1; i < M; ++i) tmp += A[i][k] * b[i];
+            b[k] -= tau * tmp;
+#pragma unroll
+            for (int i = k + 1; i < M; ++i) b[i] -= tau * A[i][k] * tmp;
+        }
+        // norm down-dating (LAPACK working note 176 style)
+#pragma unroll
+        for (int j = k + 1; j < N; ++j) {
+            if (normU[j] != 0.0) {
+                double t = fabs(A[k][j]) / normU[j];
+                t = (1.0 + t) * (1.0 - t);
+                if (t < 0.0) t = 0.0;
+                const double r = normU[j] / normD[j];
+                const double t2 = t * r * r;
+                if (t2 <= downdate_thr) {
+                    double s = 0.0;
+#pragma unroll
+                    for (int i = k + 1; i < M; ++i) s += A[i][j] * A[i][j];
+                    normD[j] = normU[j] = sqrt(s);
+                } else {
+                    normU[j] *= sqrt(t);
+                }
+            }
+        }
+    }
+    // back substitution on the leading nz x nz triangle
+    double c[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) c[i] = 0.0;
+#pragma unroll
+    for (int i = N - 1; i >= 0; --i) {
+        if (i < nz) {
+            double s = b[i];
+#pragma unroll
+            for (int j = i + 1; j < N; ++j)
+                if (j < nz) s -= A[i][j] * c[j];
+            c[i] = s / A[i][i];
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i) x[i] = 0.0;
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+        if (i < nz) {
+#pragma unroll
+            for (int t = 0; t < N; ++t)
+                if (perm[i] == t) x[t] = c[i];
+        }
 }
 
 // ---------------------------------------------------------------------------------------------
