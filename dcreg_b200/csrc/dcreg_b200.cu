@@ -205,37 +205,9 @@ __global__ void __launch_bounds__(kBlock, 3) icp_iter2_kernel(const __grid_const
     int neff = 0, npt = 0;
     unsigned n_search = 0, n_fit = 0;
     const double r2max = A.prm.search_radius * A.prm.search_radius;
-    if (!coherent) {
-        // ---- lean mode: one thread per slot, plain exact 5-NN + fit, nothing kept
-        const long long n32 = (A.n + 31) & ~31ll;             // whole warps enter the DMMA section together
-        for (long long i = (long long)blockIdx.x * blockDim.x + tid; i < n32; i += (long long)gridDim.x * blockDim.x) {
-            double px = 0.0, py = 0.0, pz = 0.0, nx = 0.0, ny = 0.0, nz = 0.0, d = 0.0;
-            bool ok = false;
-            if (i < A.n) {
-                const float4 p4 = __ldg(&A.src[i]);
-                px = (double)p4.x; py = (double)p4.y; pz = (double)p4.z;
-                // q = fl32(R p + t)  (utils.hpp:630-636)
-                const float qx = (float)(P.R[0] * px + P.R[1] * py + P.R[2] * pz + P.t[0]);
-                const float qy = (float)(P.R[3] * px + P.R[4] * py + P.R[5] * pz + P.t[1]);
-                const float qz = (float)(P.R[6] * px + P.R[7] * py + P.R[8] * pz + P.t[2]);
-                corr::Knn5 nn;
-                corr::knn_init(nn);
-                corr::knn_search(g, qx, qy, qz, nn);
-                ++n_search;
-                if (nn.pos[4] >= 0 && (double)nn.d2[4] < r2max) {            // icp_test_runner.cpp:1726
-                    npt += 1;                                                 // :1731
-                    ok = corr::fit_plane(g, nn.pos, A.prm.min_normal_norm, A.prm.plane_thickness, nx, ny, nz, d);
-                    ++n_fit;
-                }
-                if (!ok) { nx = 0.0; ny = 0.0; nz = 0.0; d = 0.0; }
-            }
-            double c[8];
-            k1::slot_front<kUseWd>(P, px, py, pz, nx, ny, nz, d, ok, c, neff);
-            __syncwarp();
-            k1::gram_accumulate_dmma(sm.tbuf[warp], lane, c, c0, c1, e0, e1);
-        }
-    } else {
-        // ---- coherent mode: 256-slot tiles, work lists per tile so that the rare searches and fits run densely
+    {
+        // ---- 256-slot tiles with per-tile work lists, so that searches and fits run densely packed.  Lean mode (the
+        // pose still moves a lot) uses the same phases: every slot searches (plain 5-NN), every accepted slot fits.
         for (long long base = (long long)blockIdx.x * kBlock; base < A.n; base += (long long)gridDim.x * kBlock) {
             const long long i = base + tid;
             const bool valid = i < A.n;
@@ -299,7 +271,7 @@ __global__ void __launch_bounds__(kBlock, 3) icp_iter2_kernel(const __grid_const
             // -- 2. searches: few -> one warp per listed slot (the other slots' threads are not held up by a
             //       15 us sequential search); many -> every thread searches for its own slot
             const int nS = sm.nS;
-            if (nS <= a.coop_max) {
+            if (coherent && nS <= a.coop_max) {
                 corr::WarpKnnSmem& W = *reinterpret_cast<corr::WarpKnnSmem*>(sm.tbuf[warp]);
                 for (int w = warp; w < nS; w += kBlock / 32) {
                     const int t = sm.listS[w];
@@ -319,12 +291,22 @@ __global__ void __launch_bounds__(kBlock, 3) icp_iter2_kernel(const __grid_const
             }
             if (valid && sm.res[tid][9] == 2) {       // too many for the list, or more than 64 candidates inside the bound
                 const float4 q = sm.q[tid];
-                corr::KnnM r;
-                float lbq = a.r2_up * 0.9999f;
-                corr::knn_search_lb(g, q.x, q.y, q.z, q.w, r, lbq);
+                if (coherent) {
+                    corr::KnnM r;
+                    float lbq = a.r2_up * 0.9999f;
+                    corr::knn_search_lb(g, q.x, q.y, q.z, q.w, r, lbq);
 #pragma unroll
-                for (int k = 0; k < corr::kSeeds; ++k) sm.res[tid][k] = r.pos[k];
-                sm.res[tid][7] = __float_as_int(lbq); sm.res[tid][8] = __float_as_int(r.d2[4]); sm.res[tid][9] = 0;
+                    for (int k = 0; k < corr::kSeeds; ++k) sm.res[tid][k] = r.pos[k];
+                    sm.res[tid][7] = __float_as_int(lbq); sm.res[tid][8] = __float_as_int(r.d2[4]);
+                } else {                              // lean: plain exact 5-NN, nothing kept for the next iteration
+                    corr::Knn5 r;
+                    corr::knn_init(r);
+                    corr::knn_search(g, q.x, q.y, q.z, r);
+#pragma unroll
+                    for (int k = 0; k < 5; ++k) sm.res[tid][k] = r.pos[k];
+                    sm.res[tid][5] = -1; sm.res[tid][6] = -1; sm.res[tid][7] = 0; sm.res[tid][8] = __float_as_int(r.d2[4]);
+                }
+                sm.res[tid][9] = 0;
             }
             // -- 3a. record; which five; cached plane?
             double nx = 0.0, ny = 0.0, nz = 0.0, d = 0.0;
@@ -335,13 +317,16 @@ __global__ void __launch_bounds__(kBlock, 3) icp_iter2_kernel(const __grid_const
 #pragma unroll
                 for (int k = 0; k < corr::kSeeds; ++k) pos[k] = sm.res[tid][k];
                 d5 = __int_as_float(sm.res[tid][8]);
-                a.nn[kNnRec * i] = make_int4(pos[0], pos[1], pos[2], pos[3]);
-                a.nn[kNnRec * i + 1] = make_int4(pos[4], pos[5], pos[6], sm.res[tid][7]);
-                if (sm.res[tid][9] == 0) {                                    // searched: remember where
-                    const float4 q = sm.q[tid];
-                    a.nn[kNnRec * i + 2] = make_int4(__float_as_int(q.x), __float_as_int(q.y), __float_as_int(q.z), 0);
+                if (coherent) {
+                    a.nn[kNnRec * i] = make_int4(pos[0], pos[1], pos[2], pos[3]);
+                    a.nn[kNnRec * i + 1] = make_int4(pos[4], pos[5], pos[6], sm.res[tid][7]);
+                    if (sm.res[tid][9] == 0) {                                // searched: remember where
+                        const float4 q = sm.q[tid];
+                        a.nn[kNnRec * i + 2] = make_int4(__float_as_int(q.x), __float_as_int(q.y), __float_as_int(q.z), 0);
+                    }
                 }
-                have5 = pos[4] >= 0;
+                // (a lean search is not bounded by the radius: its five may lie outside and then need no plane)
+                have5 = pos[4] >= 0 && (coherent || (double)d5 < r2max);
                 // The plane is a function of the five target points IN THEIR ORDER (the rows of the 5x3 system keep the
                 // reference's distance order, so the QR rounds exactly as a fresh fit would): the cache key is the
                 // ordered list.  A pure re-ranking therefore refits; the fit list keeps that cheap.
@@ -366,7 +351,7 @@ __global__ void __launch_bounds__(kBlock, 3) icp_iter2_kernel(const __grid_const
                         for (int k = 0; k < 5; ++k) sm.key[tid][k] = key[k];
                     }
                 }
-                if (!want_fit) { a.fit_state[i] = (signed char)fit; ok = fit == 2; }
+                if (!want_fit) { if (coherent) a.fit_state[i] = (signed char)fit; ok = fit == 2; }
             }
             {   // fit list of the tile
                 const unsigned bits = __ballot_sync(0xffffffffu, want_fit);
@@ -387,12 +372,14 @@ __global__ void __launch_bounds__(kBlock, 3) icp_iter2_kernel(const __grid_const
                 const int fit = corr::fit_plane_reg(g, key, A.prm.min_normal_norm, A.prm.plane_thickness, fx, fy, fz, fd) ? 2 : 1;
                 sm.plane[t] = make_double4(fx, fy, fz, fd);
                 sm.fitres[t] = (signed char)fit;
-                const long long it = base + t;
-                if (fit == 2) a.plane_cache[it] = make_double4(fx, fy, fz, fd);
-                int* kp = a.plane_key + 5 * it;
+                if (coherent) {
+                    const long long it = base + t;
+                    if (fit == 2) a.plane_cache[it] = make_double4(fx, fy, fz, fd);
+                    int* kp = a.plane_key + 5 * it;
 #pragma unroll
-                for (int k = 0; k < 5; ++k) kp[k] = key[k];
-                a.fit_state[it] = (signed char)fit;
+                    for (int k = 0; k < 5; ++k) kp[k] = key[k];
+                    a.fit_state[it] = (signed char)fit;
+                }
                 ++n_fit;
             }
             __syncthreads();
