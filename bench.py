@@ -37,6 +37,8 @@ C2_POINTS = 100_000
 C2_ITERS = 50
 C4_SLOTS = 10_000_000
 C4_RADIUS = 0.05
+C4_ICP_ITERS = 10                # fixed iterations of the sharded 10 M-point corridor registration
+C5_TRIALS = 5000                 # perturbation Monte-Carlo (BASELINE.json configs[4]), split over the ranks
 ALG_BYTES_PER_SLOT = 32          # float4 point + float4 plane
 K1_NCU_TRAFFIC_BYTES = 320.06e6 + 3.93e6   # dram read + write of one 10 M-slot K1 launch (ncu --set full, profiles/k1_r1_final_ncu_summary.txt)
 
@@ -121,57 +123,139 @@ def c2_params(default_params):
 # ------------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the oracle port on host cores
 # ------------------------------------------------------------------------------------------------
-_CPU_SCENE = {}
+def workload_config(world):
+    """The `config` object both arms print (the reference arm runs "your arm's config")."""
+    return {"workload": f"C2 synthetic cylinder pair {C2_POINTS} pts x {C2_ITERS} fixed ICP iterations per step from the published "
+                        "perturbation, method Ours (Schur detection + PCG), search_radius 1.0, weight derivative off (released default)",
+            "parallelism": "replicas (one scan pair per GPU)" if world > 1 else "1 GPU",
+            "l2": "K1 roofline inputs 320 MB > 126 MB L2; no flush needed",
+            "roofline_workload": f"C4 synthetic corridor {C4_SLOTS} slots, frozen float4 planes"}
 
 
-def cpu_icp_sample(n_points, iters, seed, thread_mode=1):
-    """Time `iters` full ICP iterations of the C/OpenMP oracle (the port of the reference loop) on the C2 scene,
-    kd-tree build excluded as in the reference's own timing (icp_test_runner.cpp:408-461).
-    thread_mode 1 = all host threads (correspondences + 27-sum reduction), 0 = reference-faithful (8 threads on
-    correspondences only, serial Jacobian build and A^T A).  Returns (seconds, threads, kind)."""
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import dcreg_oracle_c as oc
-    from dcreg_b200.scenes import make_cylinder, g2_initial_pose
-    key = (n_points, seed)
-    if key not in _CPU_SCENE:
-        pts = make_cylinder(n_points, seed=seed)
-        _CPU_SCENE[key] = (pts, oc.Scene(pts, pts))
-    pts, sc = _CPU_SCENE[key]
-    prm = oc.make_params(max_iterations=iters, fixed_iterations=True, kappa_target=10.0, use_weight_derivative=False,
-                         thread_mode=thread_mode)
-    t0 = time.perf_counter()
-    st, conv, n_it, T, _ = sc.icp_run(prm, g2_initial_pose(), want_log=False)
-    dt = time.perf_counter() - t0
-    assert st == 0 and n_it == iters
-    return dt, (8 if thread_mode == 0 else oc.max_threads()), "port"
+def host_cpu_budget():
+    """CPUs this process may really use: the affinity mask, capped by the cgroup CPU quota when there is one.
+    Returns (usable, affinity, quota or None)."""
+    aff = len(os.sched_getaffinity(0))
+    quota = None
+    try:                                               # cgroup v2
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if q != "max":
+            quota = float(q) / float(per)
+    except Exception:
+        pass
+    if quota is None:
+        try:                                           # cgroup v1
+            q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0 and per > 0:
+                quota = q / per
+        except Exception:
+            pass
+    usable = aff if quota is None else max(1, min(aff, int(quota + 0.5)))
+    return usable, aff, quota
+
+
+def pin_openmp_env(threads):
+    """Explicit OpenMP settings for the CPU arm, BEFORE libgomp is loaded: torchrun exports OMP_NUM_THREADS=1, and an
+    unset thread count makes libgomp spawn one spinning thread per visible CPU, which on a shared / quota-limited host
+    ran the same code anywhere between 2 and 700 iterations/s."""
+    os.environ["OMP_NUM_THREADS"] = str(threads)
+    os.environ["OMP_DYNAMIC"] = "false"
+    os.environ["OMP_PROC_BIND"] = "close"
+    os.environ["OMP_PLACES"] = "cores"
+    os.environ["OMP_WAIT_POLICY"] = "passive"          # a descheduled team member must not be spun on
+
+
+class CpuArm:
+    """The C/OpenMP oracle (CPU port of the reference loop; the reference binary cannot be built here: Eigen, PCL,
+    yaml-cpp, Ceres, TBB, Open3D absent and its "Ours" stage is a stub) on the C2 workload.  A step is the SAME step
+    the GPU arm runs: 50 fixed ICP iterations from the published perturbation; the kd-tree build is excluded as in
+    the reference's own timing (icp_test_runner.cpp:408-461)."""
+
+    def __init__(self, seed=42):
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        self.usable, self.aff, self.quota = host_cpu_budget()
+        pin_openmp_env(self.usable)
+        import dcreg_oracle_c as oc
+        from dcreg_b200.scenes import make_cylinder, g2_initial_pose
+        self.oc = oc
+        self.T0 = g2_initial_pose()
+        pts = make_cylinder(C2_POINTS, seed=seed)
+        self.scene = oc.Scene(pts, pts)
+        self.threads = None
+        self.calibration = []
+
+    def run(self, iters, threads, thread_mode=1):
+        prm = self.oc.make_params(max_iterations=iters, fixed_iterations=True, kappa_target=10.0,
+                                  use_weight_derivative=False, thread_mode=thread_mode, n_threads=threads)
+        t0 = time.perf_counter()
+        st, conv, n_it, T, _ = self.scene.icp_run(prm, self.T0, want_log=False)
+        dt = time.perf_counter() - t0
+        assert st == 0 and n_it == iters
+        return dt, T
+
+    def calibrate(self):
+        """Pick the OpenMP team size that is actually fastest on this host (one short sample per candidate, after a
+        cold-start sample): a visible-CPU count says nothing about SMT siblings, quotas or noisy neighbours."""
+        cands = sorted({c for c in (4, 8, 16, 24, 32, 48, 64, 96, 128, self.usable // 2, self.usable) if 1 <= c <= self.usable})
+        self.run(3, min(8, self.usable))                                   # first touch: page in the tree, spawn the pool
+        best = None
+        for c in cands:
+            self.run(2, c)
+            dt, _ = self.run(6, c)
+            rate = 6 / dt
+            self.calibration.append({"threads": c, "it_per_s": round(rate, 1)})
+            if best is None or rate > best[1]:
+                best = (c, rate)
+        self.threads = best[0]
+        return self.threads
+
+    def steps(self, n_steps, warmup):
+        for _ in range(max(1, warmup)):                                    # at least one full untimed step
+            self.run(C2_ITERS, self.threads)
+        times, T = [], None
+        for _ in range(max(1, n_steps)):
+            dt, T = self.run(C2_ITERS, self.threads)
+            times.append(dt)
+        return np.array(times), T
+
+    def faithful(self, n_steps=3):
+        """Reference-faithful threading: omp num_threads(8) on the correspondence loop only, serial Jacobian build and
+        serial A^T A (icp_test_runner.cpp:1714, 1863-1915)."""
+        th = min(8, self.usable)
+        self.run(5, th, thread_mode=0)
+        ts = [self.run(C2_ITERS, th, thread_mode=0)[0] for _ in range(n_steps)]
+        return {"value": C2_ITERS / float(np.median(ts)), "cores": th, "sample": f"median of {n_steps} steps of {C2_ITERS} iterations",
+                "note": "omp num_threads(8) on correspondences only, serial J build and A^T A (icp_test_runner.cpp:1714,1863-1915)"}
+
+    def describe(self, times):
+        med = float(np.median(times))
+        return {"value": C2_ITERS / med, "unit": "ICP iterations/s", "cores": int(self.threads), "kind": "port",
+                "sample": f"median of {len(times)} steps, each {C2_ITERS} fixed ICP iterations of the C2 workload from the initial pose "
+                          "(the GPU arm's step; kd-tree build excluded as in the reference)",
+                "step_s": {"median": med, "min": float(times.min()), "max": float(times.max()), "mean": float(times.mean())},
+                "host": {"affinity_cpus": self.aff, "cgroup_quota_cpus": self.quota, "usable_cpus": self.usable,
+                         "omp": {k: os.environ.get(k) for k in ("OMP_PROC_BIND", "OMP_PLACES", "OMP_WAIT_POLICY")}},
+                "thread_calibration": self.calibration}
 
 
 def run_reference(args, rank, world):
-    """The reference's own CPU algorithm (oracle port) on the host cores; rank 0 only."""
+    """The reference's own CPU algorithm (oracle port) on the host cores; rank 0 only (the other ranks exit 0)."""
     if rank != 0:
         return
-    sample_iters = 10
-    for _ in range(max(0, min(args.warmup, 2))):
-        cpu_icp_sample(C2_POINTS, 2, 42)
-    times = []
-    cores = 1
-    for _ in range(max(1, args.steps)):
-        sec, cores, kind = cpu_icp_sample(C2_POINTS, sample_iters, 42)
-        times.append(sec)
-    tot = float(np.sum(times))
-    value = sample_iters * len(times) / tot
-    sec0, cores0, _ = cpu_icp_sample(C2_POINTS, 5, 42, thread_mode=0)
+    arm = CpuArm(seed=42)
+    arm.calibrate()
+    times, _ = arm.steps(args.steps, args.warmup)
+    cpu = arm.describe(times)
+    cpu["reference_faithful_8_threads"] = arm.faithful()
+    value = cpu["value"]
     line = {
         "impl": "reference", "metric": "icp_iterations_per_s", "value": value, "unit": "ICP iterations/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot / len(times),
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * cpu["step_s"]["median"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"C2 synthetic cylinder pair {C2_POINTS} pts, method Ours (Schur detection + PCG), "
-                               "search_radius 1.0; CPU port of the reference loop (reference binary not buildable here)",
-                   "sample": f"{sample_iters} ICP iterations per step (the GPU arm runs {C2_ITERS} per step)"},
-        "cpu_baseline": {"value": value, "unit": "ICP iterations/s", "cores": cores, "kind": "port",
-                         "sample": f"{sample_iters} iterations x {len(times)} steps of the C2 workload, all host threads",
-                         "reference_faithful_8_threads": {"value": 5 / sec0, "cores": cores0,
-                                                          "note": "omp num_threads(8) on correspondences only, serial J build and A^T A (icp_test_runner.cpp:1714,1863-1915)"}},
+        "config": workload_config(world),
+        "timing": "value = 50 iterations / MEDIAN step time (host CPUs are shared with other tenants; min/max/mean in cpu_baseline.step_s)",
+        "cpu_baseline": cpu,
         "e2e": {"value": value, "unit": "ICP iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -291,29 +375,133 @@ def run_ours(args, rank, local_rank, world):
     achieved = ALG_BYTES_PER_SLOT * n_local / (k1_ms * 1e-3) / 1e9             # per GPU
     mpts = n_total / (k1_ms * 1e-3) / 1e6                                       # whole job
 
-    # ---------------- CPU baseline (rank 0, N = 1 only) ----------------
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        sec, cores, kind = cpu_icp_sample(C2_POINTS, 3, 42)                 # calibrate
-        it_all = int(min(200, max(10, 12.0 / (sec / 3))))                    # ~12 s of CPU work
-        sec, cores, kind = cpu_icp_sample(C2_POINTS, it_all, 42)
-        it_ref = int(min(100, max(5, it_all // 3)))
-        sec0, cores0, _ = cpu_icp_sample(C2_POINTS, it_ref, 42, thread_mode=0)
-        cpu = {"value": it_all / sec, "unit": "ICP iterations/s", "cores": cores, "kind": kind,
-               "sample": f"{it_all} ICP iterations of the C2 workload, all host threads (kd-tree build excluded, as in the reference)",
-               "reference_faithful_8_threads": {"value": it_ref / sec0, "cores": cores0, "sample": f"{it_ref} iterations",
-                                                "note": "omp num_threads(8) on correspondences only, serial J build and A^T A"}}
+    # ---------------- C4 end to end: the point-sharded 10 M-point corridor REGISTRATION (row N1) ----------------
+    # every rank holds a contiguous block of source slots and the whole target; one sum over ranks per iteration
+    # (inside the iteration kernel over peer memory when dcreg_comm_mode == 2), the solve step redundantly everywhere
+    prm4 = default_params(search_radius=C4_RADIUS, max_iterations=C4_ICP_ITERS, fixed_iterations=1, kappa_target=10.0)
+    res4 = ctx.icp_run(prm4, Tc, want_log=True)                              # warm-up (allocations, graph capture)
+    c4_runs = 3
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record(stream)
+    for _ in range(c4_runs):
+        res4 = ctx.icp_run(prm4, Tc, want_log=True)
+    f1.record(stream)
+    f1.synchronize()
+    barrier()
+    c4_ms = max_over_ranks(f0.elapsed_time(f1)) / c4_runs
+    comm_mode = ctx.comm_mode
+    sharded_ok, sharded_dT = None, None
+    ctx2 = Context(local_rank)                                               # plain context: no communicator
+    if world > 1:
+        # parity of the sharded run, on every rank: the same registration unsharded on this GPU alone
+        ctx2.set_target(scene, C4_RADIUS)
+        ctx2.set_source(scene)
+        ref4 = ctx2.icp_run(prm4, Tc, want_log=True)
+        sharded_dT = float(np.abs(res4.T - ref4.T).max())
+        ok = (res4.iterations == ref4.iterations and sharded_dT < 1e-9 and
+              all(a.n_effective == b.n_effective and a.n_corr_pt == b.n_corr_pt and abs(a.fitness - b.fitness) < 1e-12
+                  for a, b in zip(res4.logs, ref4.logs)))
+        t_ok = torch.tensor([1.0 if ok else 0.0], dtype=torch.float64, device=dev)
+        t_dT = torch.tensor([sharded_dT], dtype=torch.float64, device=dev)
+        dist.all_reduce(t_ok, op=dist.ReduceOp.MIN)
+        dist.all_reduce(t_dT, op=dist.ReduceOp.MAX)
+        # all ranks must hold the same pose bit for bit (the sums are formed in rank order everywhere)
+        t_pose = torch.from_numpy(res4.T.copy()).to(dev)
+        t_lo, t_hi = t_pose.clone(), t_pose.clone()
+        dist.all_reduce(t_lo, op=dist.ReduceOp.MIN); dist.all_reduce(t_hi, op=dist.ReduceOp.MAX)
+        same_bits = bool(torch.equal(t_lo, t_hi))
+        sharded_ok, sharded_dT = bool(t_ok.item() == 1.0) and (same_bits or comm_mode != 2), float(t_dT.item())
+        if not sharded_ok:
+            raise SystemExit(f"bench.py: sharded C4 registration does not match the single-GPU run (max |dT| {sharded_dT:.3e}, "
+                             f"identical over ranks: {same_bits})")
+    c4 = {"it_per_s": C4_ICP_ITERS / (c4_ms * 1e-3), "ms_per_iteration": c4_ms / C4_ICP_ITERS, "points": n_total,
+          "iterations_per_run": C4_ICP_ITERS, "runs_timed": c4_runs, "scaling": "strong",
+          "n_effective_last": int(res4.logs[-1].n_effective),
+          "collective": {0: None, 1: "ncclAllReduce of 32 doubles behind the iteration kernel + separate solve kernel (fallback)",
+                         2: "in-kernel: peer-memory mailboxes over NVLink in the iteration kernel's last block, solve step folded in"}[comm_mode],
+          "parity_vs_single_gpu": None if world == 1 else {"ok": sharded_ok, "max_abs_dT": sharded_dT,
+                                                           "what": "same 10 M-point registration unsharded on every rank: iteration counts, N_eff, N_pt, fitness identical, |dT| < 1e-9, pose bit-identical across ranks"}}
+
+    # ---------------- C5: perturbation Monte-Carlo, trials batched and split over the ranks (row N2) ----------------
+    from dcreg_b200.scenes import load_pcd_xyz, trial_poses
+    cyl = load_pcd_xyz(os.path.join(ROOT, "tests", "golden", "cylinder_7562.pcd"))     # the reference's shipped cloud
+    poses = trial_poses(C5_TRIALS, seed=45)
+    tlo, thi = shard_range(C5_TRIALS, rank, world)
+    prm5 = default_params(kappa_target=10.0)                                  # icp.yaml defaults: radius 1.0, 30 iterations
+    ctx2.set_target(cyl, 1.0)
+    ctx2.set_source(cyl)
+    ctx2.icp_run_batch(prm5, poses[tlo:thi])                                  # warm-up
+    stream2 = torch.cuda.ExternalStream(ctx2.stream, device=dev)
+    barrier()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    w5 = time.perf_counter()
+    g0.record(stream2)
+    trials = ctx2.icp_run_batch(prm5, poses[tlo:thi])                         # H2D of the poses, D2H of the results inside
+    g1.record(stream2)
+    g1.synchronize()
+    w5 = time.perf_counter() - w5
+    barrier()
+    c5_ms = max_over_ranks(max(g0.elapsed_time(g1), w5 * 1e3))
+    n_conv = torch.tensor([float(sum(t.converged for t in trials)), float(sum(t.iterations for t in trials))],
+                          dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(n_conv)
+    c5 = {"trials": C5_TRIALS, "trials_per_s": C5_TRIALS / (c5_ms * 1e-3), "ms": c5_ms, "scaling": "strong",
+          "trials_per_gpu": thi - tlo, "converged": int(n_conv[0].item()), "mean_iterations": float(n_conv[1].item()) / C5_TRIALS,
+          "workload": "shipped 7 562-point cylinder, t ~ U[-1,1]^3 m, rpy ~ U[-3,3]^3 deg (seed 45), icp.yaml defaults, method Ours; "
+                      "one dcreg_icp_run_batch call per rank (host poses in, host results out)"}
+    ctx2.close()
+
+    # ---------------- parity of the benchmarked configuration + CPU baseline (rank 0) ----------------
+    cpu, parity = None, None
+    if rank == 0 and not args.no_cpu_baseline:
+        import dcreg_oracle as onp                                           # se3 log distance (NumPy twin)
+        arm = CpuArm(seed=42)                                                # rank 0's scene
+        arm.calibrate()
+        n_cpu_steps = 8 if world == 1 else 1
+        times, T_cpu = arm.steps(n_cpu_steps, 1)
+        pose_err = float(onp.se3_log_distance(T_cpu, res.T))
+        parity = {"parity_checked": True, "pose_err": pose_err, "tolerance": 1e-6,
+                  "what": "|log(T_oracle^-1 T_gpu)| after the 50 fixed iterations of the timed C2 step, C/OpenMP oracle vs the e2e GPU result"}
+        if not pose_err < 1e-6:
+            raise SystemExit(f"bench.py: C2 parity FAILED, pose error {pose_err:.3e} vs the CPU oracle")
+        # C5 parity: a 16-trial sample of rank 0's trials against the C oracle
+        cyl_sc = arm.oc.Scene(cyl, cyl)
+        prm5c = arm.oc.make_params(max_iterations=30, kappa_target=10.0, n_threads=min(8, arm.usable))
+        worst5 = 0.0
+        for k in range(0, 16):
+            st5, conv5, it5, T5, _ = cyl_sc.icp_run(prm5c, poses[tlo + k], want_log=False)
+            if st5 != trials[k].status or it5 != trials[k].iterations or conv5 != trials[k].converged:
+                raise SystemExit(f"bench.py: C5 trial {k} differs from the CPU oracle (status/iterations/converged)")
+            worst5 = max(worst5, float(onp.se3_log_distance(T5, trials[k].T)))
+        if not worst5 < 1e-6:
+            raise SystemExit(f"bench.py: C5 parity FAILED, pose error {worst5:.3e}")
+        c5["parity"] = {"trials_checked": 16, "max_pose_err": worst5, "tolerance": 1e-6}
+        if world == 1:
+            cpu = arm.describe(times)
+            cpu["reference_faithful_8_threads"] = arm.faithful()
+            # C5 on the CPU: independent trials, one single-threaded oracle run per worker thread, all usable CPUs busy
+            from concurrent.futures import ThreadPoolExecutor
+            n5 = int(min(C5_TRIALS, max(2 * arm.threads, 64)))
+            prm51 = arm.oc.make_params(max_iterations=30, kappa_target=10.0, n_threads=1)
+            scenes5 = [arm.oc.Scene(cyl, cyl) for _ in range(arm.threads)]
+            def one(k):
+                return scenes5[k % arm.threads].icp_run(prm51, poses[k], want_log=False)[2]
+            with ThreadPoolExecutor(arm.threads) as ex:
+                list(ex.map(one, range(arm.threads)))                        # spin up
+                t5 = time.perf_counter()
+                list(ex.map(one, range(n5)))
+                t5 = time.perf_counter() - t5
+            c5["cpu_port"] = {"trials_per_s": n5 / t5, "workers": int(arm.threads), "sample": f"{n5} of the {C5_TRIALS} trials, "
+                              "one single-threaded oracle registration per worker thread"}
 
     if rank == 0:
         line = {
             "metric": "icp_iterations_per_s", "value": value, "unit": "ICP iterations/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"C2 synthetic cylinder pair {C2_POINTS} pts x {C2_ITERS} fixed ICP iterations per step, "
-                                   "method Ours (Schur detection + PCG), weight derivative off (released default), device grid correspondences",
-                       "parallelism": "replicas (one scan pair per GPU)" if world > 1 else "1 GPU",
-                       "l2": "K1 roofline inputs 320 MB > 126 MB L2; no flush needed",
-                       "roofline_workload": f"C4 synthetic corridor {C4_SLOTS} slots, frozen float4 planes"},
+            "config": workload_config(world),
             "e2e": {"value": e2e_value, "unit": "ICP iterations/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": int(launches),
@@ -332,9 +520,12 @@ def run_ours(args, rank, local_rank, world):
                           "f64_plane_variant_ms": k1_ms_f64,
                           "f64_plane_variant_gbs": 48 * n_local / (k1_ms_f64 * 1e-3) / 1e9,
                           "n_effective": int(stats[1]),
-                          "collective": "ncclAllReduce 32 doubles per launch (inside the timed region)" if world > 1 else None,
+                          "collective": None if world == 1 else ("sum over ranks inside K1's last block over peer memory (in the timed region)" if comm_mode == 2 else "ncclAllReduce 32 doubles per launch (inside the timed region)"),
                           "sharding": f"{world} contiguous point blocks of {n_local} slots" if world > 1 else None},
+            "sharded_icp": c4,
+            "trials": c5,
             "cpu_baseline": cpu,
+            "parity_checked": bool(parity), "pose_err": parity["pose_err"] if parity else None, "parity": parity,
             "clocks": clocks,
         }
         print(json.dumps(line))
@@ -352,6 +543,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank, local_rank, world = env_int("RANK", 0), env_int("LOCAL_RANK", 0), env_int("WORLD_SIZE", 1)
+    pin_openmp_env(host_cpu_budget()[0])       # before anything loads libgomp (torch does): see pin_openmp_env
     if args.impl == "reference":
         run_reference(args, rank, world)
     else:

@@ -58,8 +58,9 @@ class Analysis(C.Structure):
         ("lambda_sub_rot", C.c_double * 3), ("lambda_sub_trans", C.c_double * 3),
         ("schur_V_rot", C.c_double * 9), ("schur_V_trans", C.c_double * 9),
         ("aligned_V_rot", C.c_double * 9), ("aligned_V_trans", C.c_double * 9),
-        ("rot_indices", C.c_int32 * 3), ("trans_indices", C.c_int32 * 3), ("reserved1", C.c_int32 * 2),
-        ("P_preconditioner", C.c_double * 36), ("pcg_residual", C.c_double),
+        ("rot_indices", C.c_int32 * 3), ("trans_indices", C.c_int32 * 3), ("schur_singular", C.c_int32),
+        ("reserved1", C.c_int32), ("P_preconditioner", C.c_double * 36), ("W_adaptive", C.c_double * 36),
+        ("pcg_residual", C.c_double),
     ]
 
     def np(self, name):
@@ -69,7 +70,7 @@ class Analysis(C.Structure):
 class IterLog(C.Structure):
     _fields_ = [
         ("iter", C.c_int32), ("status", C.c_int32), ("n_effective", C.c_int32), ("n_corr_pt", C.c_int32),
-        ("rmse", C.c_double), ("fitness", C.c_double), ("objective", C.c_double),
+        ("rmse", C.c_double), ("fitness", C.c_double), ("objective", C.c_double), ("iter_time_ms", C.c_double),
         ("gradient", C.c_double * 6), ("H27", C.c_double * 27), ("dx", C.c_double * 6), ("T", C.c_double * 16),
         ("analysis", Analysis),
     ]
@@ -86,7 +87,7 @@ EXPORTS = [
     "dcreg_stream", "dcreg_set_source", "dcreg_set_target", "dcreg_find_planes",
     "dcreg_reduce_normal_equations", "dcreg_reduce_normal_equations_f64plane",
     "dcreg_reduce_normal_equations_host", "dcreg_analyze_and_solve", "dcreg_solve_pcg", "dcreg_icp_run",
-    "dcreg_icp_run_host_planes", "dcreg_last_covariance", "dcreg_point_to_point_metrics", "dcreg_comm_unique_id", "dcreg_comm_init",
+    "dcreg_icp_run_batch", "dcreg_icp_run_host_planes", "dcreg_comm_mode", "dcreg_last_covariance", "dcreg_point_to_point_metrics", "dcreg_comm_unique_id", "dcreg_comm_init",
     "dcreg_comm_destroy", "dcreg_set_global_source_count", "dcreg_launch_count", "dcreg_device_source",
     "dcreg_device_planes_f64", "dcreg_device_planes_f32", "dcreg_freeze_planes_f32", "dcreg_time_reduce", "dcreg_time_iteration", "dcreg_iteration_counters",
 ]
@@ -119,6 +120,9 @@ def load_library():
     lib.dcreg_solve_pcg.argtypes = [vp, dp, dp, dp, ci, C.c_double, dp, C.POINTER(ci)]
     lib.dcreg_icp_run.argtypes = [vp, C.POINTER(IcpParams), dp, dp, C.POINTER(IterLog), ci, C.POINTER(ci),
                                   C.POINTER(ci)]
+    lib.dcreg_icp_run_batch.argtypes = [vp, C.POINTER(IcpParams), ci, dp, dp, C.POINTER(ci), C.POINTER(ci), C.POINTER(ci),
+                                        C.POINTER(IterLog), ci]
+    lib.dcreg_comm_mode.argtypes = [vp]
     lib.dcreg_icp_run_host_planes.argtypes = [vp, C.POINTER(IcpParams), dp, PLANE_CALLBACK, vp, dp,
                                               C.POINTER(IterLog), ci, C.POINTER(ci), C.POINTER(ci)]
     lib.dcreg_last_covariance.argtypes = [vp, dp]
@@ -324,6 +328,28 @@ class Context:
 
     Point2PlaneICP_SO3 = icp_run
 
+    def icp_run_batch(self, params: IcpParams, T_init, want_log: bool = False):
+        """`num_runs` registrations side by side (icp_test_runner.cpp:331-345): T_init (B, 4, 4).
+        Returns a list of IcpResult, one per trial (logs only when want_log)."""
+        T_init = np.ascontiguousarray(T_init, dtype=np.float64).reshape(-1, 4, 4)
+        B = T_init.shape[0]
+        T_out = np.empty((B, 4, 4))
+        n_it = (C.c_int * B)(); conv = (C.c_int * B)(); st = (C.c_int * B)()
+        cap = int(params.max_iterations) if want_log else 0
+        logs = (IterLog * max(cap * B, 1))() if want_log else None
+        self._check(self.lib.dcreg_icp_run_batch(self._h, C.byref(params), B, _dptr(T_init), _dptr(T_out), n_it, conv, st,
+                                                 logs, cap))
+        out = []
+        for b in range(B):
+            recs = []
+            if want_log:
+                nrec = min(n_it[b], cap)
+                if st[b] == NONFINITE_UPDATE and n_it[b] < cap:
+                    nrec = n_it[b] + 1
+                recs = [logs[b * cap + i] for i in range(nrec)]
+            out.append(IcpResult(int(st[b]), bool(conv[b]), int(n_it[b]), T_out[b], recs))
+        return out
+
     def icp_run_host_planes(self, params: IcpParams, T_init, plane_fn, want_log: bool = True) -> IcpResult:
         """Same loop with caller-supplied correspondences: plane_fn(T 4x4) -> (planes (N,4) f64, n_corr_pt)."""
         T_init = np.ascontiguousarray(T_init, dtype=np.float64)
@@ -376,6 +402,11 @@ class Context:
     def comm_init(self, unique_id: bytes, rank: int, nranks: int):
         buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
         self._check(self.lib.dcreg_comm_init(self._h, buf, rank, nranks))
+
+    @property
+    def comm_mode(self) -> int:
+        """0 no communicator, 1 ncclAllReduce fallback, 2 in-kernel peer-memory all-reduce."""
+        return int(self.lib.dcreg_comm_mode(self._h))
 
     def comm_destroy(self):
         self._check(self.lib.dcreg_comm_destroy(self._h))

@@ -186,22 +186,24 @@ __global__ void grid_scatter_kernel(const float4* __restrict__ pts, int n, const
     out[pos] = p;
 }
 
-// deterministic order inside every cell: sort by original index (insertion sort, cells are small)
-__global__ void grid_sort_cells_kernel(float4* pts, const int* __restrict__ start, const int* __restrict__ count,
-                                       const int* __restrict__ start_next, long long ncells) {
-    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= ncells) return;
+// Deterministic order inside every cell: ascending original index.  The scatter above fills a cell in atomic-arrival
+// order; this pass moves every point to (cell start + number of points of its cell with a smaller index).  One thread
+// per point, O(points in its cell) reads of a range its neighbours read too - parallel over POINTS, so a cell with
+// thousands of points (dense map, cell = search radius) no longer serialises on one thread the way a per-cell insertion
+// sort does.  `cell_of` is indexed by the original point index (p.w): dense cell id or hash slot.
+__global__ void grid_rank_cells_kernel(const float4* __restrict__ in, int n, const int* __restrict__ cell_of,
+                                       const int* __restrict__ start, const int* __restrict__ count,
+                                       float4* __restrict__ out) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const float4 p = in[j];
+    const int me = __float_as_int(p.w);
+    const int c = cell_of[me];
     const int s = start[c];
-    const int cnt = count ? count[c] : (start_next[c] - s);
-    if (cnt < 2) return;
-    float4* p = pts + s;
-    for (int i = 1; i < cnt; ++i) {
-        const float4 v = p[i];
-        const int key = __float_as_int(v.w);
-        int j = i - 1;
-        while (j >= 0 && __float_as_int(p[j].w) > key) { p[j + 1] = p[j]; --j; }
-        p[j + 1] = v;
-    }
+    const int e = count ? s + count[c] : start[c + 1];
+    int rank = 0;
+    for (int k = s; k < e; ++k) rank += (__float_as_int(__ldg(&in[k].w)) < me) ? 1 : 0;
+    out[s + rank] = p;
 }
 
 // cell of a (transformed) source point for the spatial sort of the source cloud, clamped into the target box

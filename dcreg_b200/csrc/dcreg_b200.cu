@@ -26,6 +26,7 @@
 #include "k1_reduce.cuh"
 #include "k1_stream.cuh"
 #include "k2_solve.cuh"
+#include "peer_reduce.cuh"
 
 using k2::IcpState;
 using k2::kAcc;
@@ -64,6 +65,24 @@ __device__ __forceinline__ bool last_block_ticket(unsigned int* counter) {
     __syncthreads();
     if (is_last) __threadfence();
     return is_last;
+}
+
+// K2 executed by warp 0 of the block that finished a trial's reduction (k2_solve.cuh).  A separate function with its
+// own register allocation and stack frame: the iteration kernels are capped at 85 registers for 3 blocks per SM and
+// must not pay for the solve's live state.  acc: the body-frame sums in shared memory.
+static_assert(sizeof(k2::WarpSmem) <= 8 * k1::kTRow * sizeof(double), "k2::WarpSmem must fit one warp's transpose buffer");
+__device__ __noinline__ void solve_step_in_kernel(const double* acc, IcpState* st, const dcreg_icp_params* prm,
+                                                  dcreg_iter_log* log, int log_cap, k2::WarpSmem* sm, const float* src_radius,
+                                                  double coherent_step, unsigned int* n_active) {
+    // only the "Ours" method (Schur detection + PCG, the warp-cooperative step) is folded; the baseline methods' generic
+    // single-thread step needs a 3.7 KB stack frame, which every thread of the iteration kernel would have to reserve:
+    // they keep the separate solve kernel (k2_step_kernel)
+    const int lane = threadIdx.x & 31;
+    const double lever = src_radius ? (double)*src_radius : 1.0e30;
+    const double max_step = coherent_step * prm->search_radius;
+    k2::icp_step_warp_ours(acc, st, *prm, log, log_cap, *sm, lever, max_step);         // all 32 lanes cooperate
+    __syncwarp();
+    if (lane == 0 && n_active && st->done) atomicSub(n_active, 1u);
 }
 
 struct IterArgs {
@@ -118,7 +137,7 @@ __global__ void __launch_bounds__(kBlock, 3) icp_iteration_kernel(const __grid_c
                 a.planes_out[__float_as_int(p4.w)] = ok ? make_double4(nx, ny, nz, d) : make_double4(0.0, 0.0, 0.0, 0.0);
         }
         double c[8];
-        k1::slot_front<kUseWd>(P, px, py, pz, nx, ny, nz, d, ok, c, neff);
+        k1::slot_front<kUseWd>(P, px, py, pz, nx, ny, nz, d, ok, c, neff, a.prm.weight_slope, a.prm.weight_gate);
         __syncwarp();
         k1::gram_accumulate_dmma(sm.tbuf[warp], lane, c, c0, c1, e0, e1);
     }
@@ -151,7 +170,8 @@ constexpr double kCoherentStep = 0.05;        // records are used once no source
 constexpr int kSearchListMax = 96;            // more searching slots than this in a 256-slot tile: every thread searches for itself
 
 struct Iter2Smem {
-    double tbuf[kBlock / 32][8 * k1::kTRow];    // per-warp DMMA transpose buffers (also: corr::WarpKnnSmem, the warp's Gram)
+    double tbuf[kBlock / 32][8 * k1::kTRow];    // per-warp DMMA transpose buffers (also: corr::WarpKnnSmem, the warp's Gram,
+                                                // and - in the last block, after the reduction - k2::WarpSmem)
     k1s::TailSmem tail;
     // coherent mode, per 256-slot tile
     float4 q[kBlock];                           // query (x, y, z), w = search bound B
@@ -163,12 +183,24 @@ struct Iter2Smem {
     int nS, nF;
 };
 
+// Grid = (blocks per trial, trials).  A trial is one registration (one initial pose) of the context's source against
+// its target (icp_test_runner.cpp:331-345 runs `num_runs` of them back to back; dcreg_icp_run_batch runs them side by
+// side).  Everything a trial owns is an array indexed by blockIdx.y: loop state, ticket, partials, sums, neighbour
+// records, plane cache, log.  dcreg_icp_run is the one-trial case.
 struct Iter2Args {
-    IterArgs it;
-    int4* nn;                 // [kNnRec n] neighbour records
-    double4* plane_cache;     // plane fitted to the slot's current five neighbours (reused while the set stays)
-    signed char* fit_state;   // 0 = nothing cached, 1 = cached fit failed its gates, 2 = cached plane valid
-    int* plane_key;           // [5 n] the five positions (in distance order) the cached plane was fitted to
+    IterArgs it;              // it.state / it.partials / it.counter / it.acc: per-trial arrays ([B], [B][grid.x][32], [B], [B][32])
+    int4* nn;                 // [B][kNnRec n] neighbour records
+    double4* plane_cache;     // [B][n] plane fitted to the slot's current five neighbours (reused while the set stays)
+    signed char* fit_state;   // [B][n] 0 = nothing cached, 1 = cached fit failed its gates, 2 = cached plane valid
+    int* plane_key;           // [B][5 n] the five positions (in distance order) the cached plane was fitted to
+    // the solve / update step (K2) runs in the last block of every trial: no second launch, no host, no acc round trip
+    int fold_k2;              // 0: stop after writing the sums (sharded run over NCCL: all-reduce + k2_step_kernel follow)
+    dcreg_iter_log* log;      // [B][log_cap] or null
+    int log_cap;
+    const float* src_radius;  // max |p| over the source (lever arm of a rotation step)
+    double coherent_step;
+    unsigned int* n_active;   // trials still running (decremented by the step that finishes one); host polls it
+    peer::View peer;          // multi-GPU: the sum over ranks, inside the last block (peer_reduce.cuh)
     int coop_max;             // more searching slots than this in a tile: every thread searches for itself (kSearchListMax)
     int force;                // 0: mode and seeds from the loop state (written by K2); 1: coherent mode, seeds = use_seeds
     int use_seeds;            // (force) records of the previous launch are valid
@@ -190,17 +222,24 @@ __global__ void __launch_bounds__(kBlock, 3) icp_iter2_kernel(const __grid_const
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Iter2Smem& sm = *reinterpret_cast<Iter2Smem*>(smem_raw);
     const IterArgs& A = a.it;
-    pdl_wait();                                   // the pose / mode flags come from the previous solve kernel
+    pdl_wait();                                   // the pose / mode flags come from the previous iteration's solve step
     pdl_release();
-    if (A.state->done) return;
+    const int trial = (int)blockIdx.y;
+    IcpState* const st = A.state + trial;
+    if (st->done) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const k1::Pose P = load_pose(A.state);
+    const k1::Pose P = load_pose(st);
     const corr::Grid& g = A.grid;
+    // this trial's slices of the per-slot records
+    int4* const rec_nn = a.nn + (size_t)trial * kNnRec * A.n;
+    double4* const rec_plane = a.plane_cache + (size_t)trial * A.n;
+    signed char* const rec_fit = a.fit_state + (size_t)trial * A.n;
+    int* const rec_key = a.plane_key + (size_t)trial * 5 * A.n;
     // mode (uniform over the grid): while the pose still moves by more than ~5 % of the search radius per iteration
     // nothing can be reused; the lean path (plain 5-NN search, no records) is ~25 % cheaper than searching with a
     // certificate.  K2 flips `coherent` from the size of its update.
-    const bool coherent = a.force ? true : (A.state->coherent != 0);
-    const bool use_seeds = a.force ? (a.use_seeds != 0) : (coherent && A.state->seeds != 0);
+    const bool coherent = a.force ? true : (st->coherent != 0);
+    const bool use_seeds = a.force ? (a.use_seeds != 0) : (coherent && st->seeds != 0);
     double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;
     int neff = 0, npt = 0;
     unsigned n_search = 0, n_fit = 0;
@@ -226,9 +265,9 @@ __global__ void __launch_bounds__(kBlock, 3) icp_iter2_kernel(const __grid_const
                 float B = a.r2_up;
                 need = true;
                 if (use_seeds) {
-                    const int4 s0 = a.nn[kNnRec * i], s1 = a.nn[kNnRec * i + 1];
+                    const int4 s0 = rec_nn[kNnRec * i], s1 = rec_nn[kNnRec * i + 1];
                     if (s1.z >= 0) {                                          // all seven seeds exist
-                        const int4 s2 = a.nn[kNnRec * i + 2];
+                        const int4 s2 = rec_nn[kNnRec * i + 2];
                         corr::KnnM nn;
                         nn.pos[0] = s0.x; nn.pos[1] = s0.y; nn.pos[2] = s0.z; nn.pos[3] = s0.w;
                         nn.pos[4] = s1.x; nn.pos[5] = s1.y; nn.pos[6] = s1.z;
@@ -318,11 +357,11 @@ __global__ void __launch_bounds__(kBlock, 3) icp_iter2_kernel(const __grid_const
                 for (int k = 0; k < corr::kSeeds; ++k) pos[k] = sm.res[tid][k];
                 d5 = __int_as_float(sm.res[tid][8]);
                 if (coherent) {
-                    a.nn[kNnRec * i] = make_int4(pos[0], pos[1], pos[2], pos[3]);
-                    a.nn[kNnRec * i + 1] = make_int4(pos[4], pos[5], pos[6], sm.res[tid][7]);
+                    rec_nn[kNnRec * i] = make_int4(pos[0], pos[1], pos[2], pos[3]);
+                    rec_nn[kNnRec * i + 1] = make_int4(pos[4], pos[5], pos[6], sm.res[tid][7]);
                     if (sm.res[tid][9] == 0) {                                // searched: remember where
                         const float4 q = sm.q[tid];
-                        a.nn[kNnRec * i + 2] = make_int4(__float_as_int(q.x), __float_as_int(q.y), __float_as_int(q.z), 0);
+                        rec_nn[kNnRec * i + 2] = make_int4(__float_as_int(q.x), __float_as_int(q.y), __float_as_int(q.z), 0);
                     }
                 }
                 // (a lean search is not bounded by the radius: its five may lie outside and then need no plane)
@@ -335,12 +374,12 @@ __global__ void __launch_bounds__(kBlock, 3) icp_iter2_kernel(const __grid_const
                 if (have5) {
                     int cached = 0;
                     if (use_seeds) {
-                        const int* kp = a.plane_key + 5 * i;
+                        const int* kp = rec_key + 5 * i;
                         if (kp[0] == key[0] && kp[1] == key[1] && kp[2] == key[2] && kp[3] == key[3] && kp[4] == key[4])
-                            cached = (int)a.fit_state[i];
+                            cached = (int)rec_fit[i];
                     }
                     if (cached == 2) {
-                        const double4 c = a.plane_cache[i];
+                        const double4 c = rec_plane[i];
                         nx = c.x; ny = c.y; nz = c.z; d = c.w;
                         fit = 2;
                     } else if (cached == 1) {
@@ -351,7 +390,7 @@ __global__ void __launch_bounds__(kBlock, 3) icp_iter2_kernel(const __grid_const
                         for (int k = 0; k < 5; ++k) sm.key[tid][k] = key[k];
                     }
                 }
-                if (!want_fit) { if (coherent) a.fit_state[i] = (signed char)fit; ok = fit == 2; }
+                if (!want_fit) { if (coherent) rec_fit[i] = (signed char)fit; ok = fit == 2; }
             }
             {   // fit list of the tile
                 const unsigned bits = __ballot_sync(0xffffffffu, want_fit);
@@ -374,11 +413,11 @@ __global__ void __launch_bounds__(kBlock, 3) icp_iter2_kernel(const __grid_const
                 sm.fitres[t] = (signed char)fit;
                 if (coherent) {
                     const long long it = base + t;
-                    if (fit == 2) a.plane_cache[it] = make_double4(fx, fy, fz, fd);
-                    int* kp = a.plane_key + 5 * it;
+                    if (fit == 2) rec_plane[it] = make_double4(fx, fy, fz, fd);
+                    int* kp = rec_key + 5 * it;
 #pragma unroll
                     for (int k = 0; k < 5; ++k) kp[k] = key[k];
-                    a.fit_state[it] = (signed char)fit;
+                    rec_fit[it] = (signed char)fit;
                 }
                 ++n_fit;
             }
@@ -395,7 +434,7 @@ __global__ void __launch_bounds__(kBlock, 3) icp_iter2_kernel(const __grid_const
                 if (!ok) { nx = 0.0; ny = 0.0; nz = 0.0; d = 0.0; }
             }
             double c[8];
-            k1::slot_front<kUseWd>(P, px, py, pz, nx, ny, nz, d, ok, c, neff);
+            k1::slot_front<kUseWd>(P, px, py, pz, nx, ny, nz, d, ok, c, neff, A.prm.weight_slope, A.prm.weight_gate);
             __syncwarp();
             k1::gram_accumulate_dmma(sm.tbuf[warp], lane, c, c0, c1, e0, e1);
             __syncthreads();
@@ -429,7 +468,16 @@ __global__ void __launch_bounds__(kBlock, 3) icp_iter2_kernel(const __grid_const
     else if (lane == k1s::kPkB2) mine = G[6 * 8 + 6];
     else if (lane == k1s::kPkNeff) mine = (double)neff;
     else if (lane == k1s::kPkNpt) mine = (double)npt;
-    k1s::finish_packed(mine, sm.tail, A.partials, A.counter, A.state->R, A.acc);
+    // ---- grid reduction of this trial, [sum over ranks], congruence, solve + pose update: all in the last block
+    if (!k1s::reduce_to_fin(mine, sm.tail, A.partials + (size_t)trial * gridDim.x * k1s::kPk, A.counter + trial,
+                            (int)blockIdx.x, (int)gridDim.x)) return;
+    peer::all_reduce32(a.peer, sm.tail.fin, sm.tail.red);
+    k1s::congruence(sm.tail.fin, st->R, sm.tail.acc);
+    __syncthreads();
+    if (tid < kAcc) A.acc[(size_t)trial * kAcc + tid] = sm.tail.acc[tid];
+    if (a.fold_k2 && warp == 0)
+        solve_step_in_kernel(sm.tail.acc, st, &A.prm, a.log ? a.log + (size_t)trial * a.log_cap : nullptr, a.log_cap,
+                             reinterpret_cast<k2::WarpSmem*>(sm.tbuf[0]), a.src_radius, a.coherent_step, a.n_active);
 }
 
 // K2 as its own kernel (seam 3, and the sharded loop after the all-reduce).
@@ -444,12 +492,16 @@ struct K2Scratch {
     IcpState state;
 };
 
-__global__ void __launch_bounds__(32) k2_step_kernel(const double* acc, IcpState* st, dcreg_icp_params prm,
-                                                     dcreg_iter_log* log, int log_cap, const float* src_radius,
-                                                     double coherent_step, K2Scratch* scratch) {
+// One warp per trial (blockIdx.x): acc_all [B][kAcc], st_all [B], log_all [B][log_cap].  scratch (rehearsal) only for B = 1.
+__global__ void __launch_bounds__(32) k2_step_kernel(const double* acc_all, IcpState* st_all, dcreg_icp_params prm,
+                                                     dcreg_iter_log* log_all, int log_cap, const float* src_radius,
+                                                     double coherent_step, K2Scratch* scratch, unsigned int* n_active) {
     __shared__ k2::WarpSmem sm;
     pdl_release();
     const int lane = threadIdx.x;
+    const double* acc = acc_all + (size_t)blockIdx.x * kAcc;
+    IcpState* st = st_all + blockIdx.x;
+    dcreg_iter_log* log = log_all ? log_all + (size_t)blockIdx.x * log_cap : nullptr;
     const double max_step = coherent_step * prm.search_radius;
     const bool warp_path = prm.detection == DCREG_DET_SCHUR_CONDITION_NUMBER && prm.handling == DCREG_HAND_PRECONDITIONED_CG;
 #pragma unroll 1
@@ -475,6 +527,7 @@ __global__ void __launch_bounds__(32) k2_step_kernel(const double* acc, IcpState
         }
         __syncwarp();
         if (pass == 1 && scratch) scratch->acc_prev[lane] = acc[lane];              // kAcc == 32: next launch's rehearsal input
+        if (pass == 1 && lane == 0 && n_active && st->done) atomicSub(n_active, 1u);
     }
 }
 
@@ -486,8 +539,10 @@ __global__ void k2_analyze_kernel(const double* v27, dcreg_icp_params prm, dcreg
 // Post-run log fill: one thread per iteration record recomputes the FULL analysis from the record's H27
 // (same code, same inputs => identical mask / P / PCG counts as the in-loop critical path wrote) and thereby adds the
 // log-only quantities without putting them on the loop's critical path.
-__global__ void log_fill_kernel(dcreg_iter_log* log, int log_cap, const IcpState* st, dcreg_icp_params prm) {
+__global__ void log_fill_kernel(dcreg_iter_log* logs, int log_cap, const IcpState* states, dcreg_icp_params prm) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const IcpState* st = states + blockIdx.y;
+    dcreg_iter_log* log = logs + (size_t)blockIdx.y * log_cap;
     const int n = st->iter < log_cap ? st->iter : log_cap;
     if (i >= n) return;
     if (log[i].status != DCREG_OK) return;
@@ -561,17 +616,24 @@ __global__ void flush_l2_kernel(float4* buf, long long n, float v) {
         buf[i] = make_float4(v, v, v, v);
 }
 
-__global__ void init_state_kernel(IcpState* st, const double* T, long long n_total, unsigned int* counter) {
-    if (threadIdx.x != 0) return;
+// one thread per trial: T = [n_trials][16] row-major 4x4 initial poses
+__global__ void init_state_kernel(IcpState* states, const double* T, long long n_total, unsigned int* counters, int n_trials,
+                                  unsigned int* n_active) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b == 0 && n_active) *n_active = (unsigned)n_trials;
+    if (b >= n_trials) return;
+    IcpState* st = states + b;
+    const double* Tb = T + (size_t)b * 16;
     for (int r = 0; r < 3; ++r) {
-        for (int c = 0; c < 3; ++c) st->R[r * 3 + c] = T[r * 4 + c];
-        st->t[r] = T[r * 4 + 3];
+        for (int c = 0; c < 3; ++c) st->R[r * 3 + c] = Tb[r * 4 + c];
+        st->t[r] = Tb[r * 4 + 3];
     }
     st->iter = 0; st->done = 0; st->converged = 0; st->status = DCREG_OK;
     for (int i = 0; i < 36; ++i) st->H_last[i] = (i % 7 == 0) ? 1.0 : 0.0;
     st->n_source_total = n_total;
-    st->step_rot = 1.0e30; st->step_trans = 1.0e30; st->seeds = 0; st->coherent_used = 0; st->coherent = 0;
-    *counter = 0u;
+    st->step_rot = 1.0e30; st->step_trans = 1.0e30; st->seeds = 0; st->coherent_used = 0; st->coherent = 0; st->pad0 = 0;
+    st->t_last = k2::globaltimer_ns();                      // tic of iteration 0 (icp_test_runner.cpp:1695)
+    counters[b] = 0u;
 }
 
 }  // namespace
@@ -588,6 +650,7 @@ struct NcclApi {
     int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
     int (*CommDestroy)(ncclComm_t) = nullptr;
     int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
     bool load(std::string& err) {
         if (lib) return true;
@@ -601,6 +664,7 @@ struct NcclApi {
         CommInitRank = (int (*)(ncclComm_t*, int, ncclUniqueId, int))dlsym(lib, "ncclCommInitRank");
         CommDestroy = (int (*)(ncclComm_t))dlsym(lib, "ncclCommDestroy");
         AllReduce = (int (*)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t))dlsym(lib, "ncclAllReduce");
+        AllGather = (int (*)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t))dlsym(lib, "ncclAllGather");
         GetErrorString = (const char* (*)(int))dlsym(lib, "ncclGetErrorString");
         if (!GetUniqueId || !CommInitRank || !CommDestroy || !AllReduce) { err = "libnccl: missing symbols"; return false; }
         return true;
@@ -608,6 +672,7 @@ struct NcclApi {
 };
 NcclApi g_nccl;
 constexpr int kNcclFloat64 = 8;   // ncclDouble
+constexpr int kNcclInt8 = 0;      // ncclInt8 / ncclChar
 constexpr int kNcclSum = 0;
 }  // namespace
 
@@ -633,6 +698,7 @@ struct dcreg_ctx {
     unsigned int* d_iter_stats = nullptr;                                  // optional profiling counters of the iteration kernel
     int4* d_nn = nullptr; long long nn_cap = 0; bool nn_valid = false;   // neighbours of the sorted source (seeds of the next iteration)
     float4* d_src_sorted = nullptr; long long src_sorted_cap = 0;     // source in target-cell order (w = original index)
+    float4* d_sort_tmp = nullptr;                                     // ... before the in-cell ranking
     int* d_cell_tmp = nullptr; long long cell_tmp_cap = 0;            // counts / fill cursors for the source sort
     int* d_pt_cell = nullptr; long long pt_cell_cap = 0;
     int* d_tile_sums = nullptr; long long tile_sums_cap = 0;
@@ -640,11 +706,20 @@ struct dcreg_ctx {
 
     double4* d_planes64 = nullptr; float4* d_planes32 = nullptr; long long planes_cap = 0;
 
+    // per-trial arrays (dcreg_icp_run = 1 trial, dcreg_icp_run_batch = many): [trials_cap] each
+    int trials_cap = 0;
     double* d_partials = nullptr; int partials_blocks = 0;
     unsigned int* d_counter = nullptr;
     double* d_acc = nullptr;
     IcpState* d_state = nullptr;
-    dcreg_iter_log* d_log = nullptr; int log_cap = 0;
+    unsigned int* d_n_active = nullptr;   // trials still running
+    double* d_T_init = nullptr; int T_init_cap = 0;
+    int nn_trials = 0;                    // trials the per-slot record arrays (d_nn, d_plane_cache, ...) are sized for
+    dcreg_iter_log* d_log = nullptr; long long log_cap = 0;   // records, [trials][log_cap of the run]
+    bool loop_attr_done = false, k1_attr_done[8] = {false, false, false, false, false, false, false, false};
+    // CUDA graph of one chunk of loop iterations (keyed on the kernel arguments)
+    cudaGraphExec_t graph_exec = nullptr; std::vector<unsigned char> graph_key; bool graph_off = false;
+    long long graph_launches = 0;
     double* d_small = nullptr;       // scratch for the seams (>= 512 doubles)
     K2Scratch* d_k2_scratch = nullptr;   // K2's rehearsal state (see k2_step_kernel)
     dcreg_analysis* d_analysis = nullptr;
@@ -653,6 +728,9 @@ struct dcreg_ctx {
     void* h_pinned = nullptr; size_t pinned_bytes = 0;
 
     ncclComm_t comm = nullptr; int rank = 0, nranks = 1;
+    // peer mailboxes for the in-kernel sum over ranks (peer_reduce.cuh); NCCL all-reduce is the fallback
+    peer::Mailbox* d_mailbox = nullptr; void* peer_ptr[peer::kMaxRanks] = {nullptr}; bool peer_ok = false;
+    peer::View peer_view{};
 };
 
 namespace {
@@ -695,12 +773,30 @@ int ensure_planes(dcreg_ctx* ctx, long long n) {
     return DCREG_OK;
 }
 
-int ensure_log(dcreg_ctx* ctx, int cap) {
-    if (ctx->log_cap >= cap) return DCREG_OK;
+int ensure_log(dcreg_ctx* ctx, long long records) {
+    if (ctx->log_cap >= records) return DCREG_OK;
     if (ctx->d_log) cudaFree(ctx->d_log);
     ctx->d_log = nullptr; ctx->log_cap = 0;
-    CK(cudaMalloc(&ctx->d_log, (size_t)cap * sizeof(dcreg_iter_log)));
-    ctx->log_cap = cap;
+    CK(cudaMalloc(&ctx->d_log, (size_t)records * sizeof(dcreg_iter_log)));
+    ctx->log_cap = records;
+    return DCREG_OK;
+}
+
+// per-trial loop state: IcpState, ticket, sums, initial poses
+int ensure_trials(dcreg_ctx* ctx, int trials) {
+    if (ctx->trials_cap >= trials) return DCREG_OK;
+    void* old[] = {ctx->d_counter, ctx->d_acc, ctx->d_state, ctx->d_T_init};
+    for (void* p : old)
+        if (p) cudaFree(p);
+    ctx->d_counter = nullptr; ctx->d_acc = nullptr; ctx->d_state = nullptr; ctx->d_T_init = nullptr; ctx->trials_cap = 0;
+    CK(cudaMalloc(&ctx->d_counter, (size_t)trials * sizeof(unsigned int)));
+    CK(cudaMemsetAsync(ctx->d_counter, 0, (size_t)trials * sizeof(unsigned int), ctx->stream));
+    CK(cudaMalloc(&ctx->d_acc, (size_t)trials * kAcc * sizeof(double)));
+    CK(cudaMalloc(&ctx->d_state, (size_t)trials * sizeof(IcpState)));
+    CK(cudaMemsetAsync(ctx->d_state, 0, (size_t)trials * sizeof(IcpState), ctx->stream));
+    CK(cudaMalloc(&ctx->d_T_init, (size_t)trials * 16 * sizeof(double)));
+    ctx->trials_cap = trials;
+    if (ctx->graph_exec) { cudaGraphExecDestroy(ctx->graph_exec); ctx->graph_exec = nullptr; ctx->graph_key.clear(); }
     return DCREG_OK;
 }
 
@@ -746,7 +842,8 @@ template <typename PlaneT, bool kUseWd, int kTeamCtas>
 int launch_reduce_k(dcreg_ctx* ctx, k1s::Args& a, int g) {
     auto kern = k1s::reduce_stream_kernel<PlaneT, kUseWd, kTeamCtas>;
     const size_t smem = sizeof(k1s::Smem<PlaneT>);
-    static bool configured = false;
+    // function attributes are per device: one flag per context (= per device) and kernel variant, not per process
+    bool& configured = ctx->k1_attr_done[(sizeof(PlaneT) == 32 ? 2 : 0) + (kUseWd ? 1 : 0)];
     if (!configured) {
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -773,21 +870,25 @@ int launch_reduce_t(dcreg_ctx* ctx, k1s::Args& a) {
     return launch_reduce_k<PlaneT, kUseWd, 1>(ctx, a, (int)g);
 }
 
+// slope / gate: dcreg_icp_params::weight_slope / weight_gate (0.9 / 0.1 in the reference, icp_test_runner.cpp:1776, 1785)
 int launch_reduce(dcreg_ctx* ctx, const float4* d_src, const void* d_plane, bool f64, long long n,
-                  const k1::Pose* pose, int use_wd) {
+                  const k1::Pose* pose, int use_wd, double slope = 0.9, double gate = 0.1, double npt_override = -1.0) {
     k1s::Args a{};
     a.src = d_src; a.plane = d_plane; a.n = n;
     if (pose) a.pose = *pose;
     for (int i = 0; i < 9; ++i) a.Rs[i] = ldexp(a.pose.R[i], 896);      // exact: see k1s::f32_raw
-    a.slope = 0.9; a.gate = 0.1;                                        // icp_test_runner.cpp:1776, 1785
+    a.slope = slope; a.gate = gate;
+    a.npt_override = npt_override;
+    if (ctx->peer_ok) a.peer = ctx->peer_view;                          // the sum over ranks happens inside the kernel
     { static int dbg = -1; if (dbg < 0) { const char* e = getenv("DCREG_K1_DEBUG"); dbg = e ? atoi(e) : 0; } a.debug = dbg; }
     a.counter = ctx->d_counter; a.acc = ctx->d_acc;
     if (use_wd) return f64 ? launch_reduce_t<double4, true>(ctx, a) : launch_reduce_t<float4, true>(ctx, a);
     return f64 ? launch_reduce_t<double4, false>(ctx, a) : launch_reduce_t<float4, false>(ctx, a);
 }
 
+// Fallback exchange (no peer mapping): one ncclAllReduce of the 32 sums behind the reducing kernel.
 int nccl_allreduce_acc(dcreg_ctx* ctx) {
-    if (!ctx->comm) return DCREG_OK;
+    if (!ctx->comm || ctx->peer_ok) return DCREG_OK;
     int r = g_nccl.AllReduce(ctx->d_acc, ctx->d_acc, kAcc, kNcclFloat64, kNcclSum, ctx->comm, ctx->stream);
     if (r != 0) {
         ctx->err = std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error");
@@ -796,33 +897,47 @@ int nccl_allreduce_acc(dcreg_ctx* ctx) {
     return DCREG_OK;
 }
 
-int read_results(dcreg_ctx* ctx, double* T_out, dcreg_iter_log* log, int log_cap, int* n_iterations,
+// Results of `trials` registrations: final poses, iteration counts, flags, and up to log_cap records per trial.
+// status_out[t] = dcreg_status of trial t.
+int read_results(dcreg_ctx* ctx, int trials, double* T_out, dcreg_iter_log* log, int log_cap, int* n_iterations,
                  int* converged, int* status_out) {
-    int rc = ensure_pinned(ctx, sizeof(IcpState));
+    int rc = ensure_pinned(ctx, (size_t)trials * sizeof(IcpState));
     if (rc) return rc;
     IcpState* hs = (IcpState*)ctx->h_pinned;
-    CK(cudaMemcpyAsync(hs, ctx->d_state, sizeof(IcpState), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(hs, ctx->d_state, (size_t)trials * sizeof(IcpState), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    const int iters = hs->iter;
-    if (T_out) {
-        for (int r = 0; r < 3; ++r) {
-            for (int c = 0; c < 3; ++c) T_out[r * 4 + c] = hs->R[r * 3 + c];
-            T_out[r * 4 + 3] = hs->t[r];
+    for (int t = 0; t < trials; ++t) {
+        if (T_out) {
+            double* To = T_out + (size_t)t * 16;
+            for (int r = 0; r < 3; ++r) {
+                for (int c = 0; c < 3; ++c) To[r * 4 + c] = hs[t].R[r * 3 + c];
+                To[r * 4 + 3] = hs[t].t[r];
+            }
+            To[12] = To[13] = To[14] = 0.0; To[15] = 1.0;
         }
-        T_out[12] = T_out[13] = T_out[14] = 0.0; T_out[15] = 1.0;
+        if (n_iterations) n_iterations[t] = hs[t].iter;
+        if (converged) converged[t] = hs[t].converged;
+        if (status_out) status_out[t] = hs[t].status;
     }
-    if (n_iterations) *n_iterations = iters;
-    if (converged) *converged = hs->converged;
-    *status_out = hs->status;
     if (log && log_cap > 0) {
-        int nrec = iters < log_cap ? iters : log_cap;
-        // a NOT_ENOUGH_POINTS abort still wrote a record at index iters-1; a NONFINITE abort at index iters
-        if (hs->status == DCREG_NONFINITE_UPDATE && iters < log_cap) nrec = iters + 1;
-        if (nrec > 0) {
-            CK(cudaMemcpyAsync(log, ctx->d_log, (size_t)nrec * sizeof(dcreg_iter_log), cudaMemcpyDeviceToHost,
+        if (trials == 1) {
+            const int iters = hs[0].iter;
+            int nrec = iters < log_cap ? iters : log_cap;
+            // a NOT_ENOUGH_POINTS abort still wrote a record at index iters-1; a NONFINITE abort at index iters
+            if (hs[0].status == DCREG_NONFINITE_UPDATE && iters < log_cap) nrec = iters + 1;
+            if (nrec > 0)
+                CK(cudaMemcpyAsync(log, ctx->d_log, (size_t)nrec * sizeof(dcreg_iter_log), cudaMemcpyDeviceToHost, ctx->stream));
+        } else {
+            CK(cudaMemcpyAsync(log, ctx->d_log, (size_t)trials * log_cap * sizeof(dcreg_iter_log), cudaMemcpyDeviceToHost,
                                ctx->stream));
-            CK(cudaStreamSynchronize(ctx->stream));
         }
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    if (ctx->peer_ok) {                                 // a peer that never posted (timeout in peer::all_reduce32)
+        unsigned int perr = 0;
+        CK(cudaMemcpyAsync(&perr, &ctx->d_mailbox->error, sizeof(perr), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        if (perr) { ctx->err = "peer all-reduce timed out waiting for rank " + std::to_string((int)perr - 1); return DCREG_NCCL_ERROR; }
     }
     return DCREG_OK;
 }
@@ -863,11 +978,12 @@ int dcreg_create(int device_id, dcreg_ctx** out) {
     CK(cudaGetDeviceProperties(&prop, device_id));
     ctx->sm_count = prop.multiProcessorCount;
     CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-    CK(cudaMalloc(&ctx->d_counter, sizeof(unsigned int)));
-    CK(cudaMemsetAsync(ctx->d_counter, 0, sizeof(unsigned int), ctx->stream));
-    CK(cudaMalloc(&ctx->d_acc, kAcc * sizeof(double)));
-    CK(cudaMalloc(&ctx->d_state, sizeof(IcpState)));
-    CK(cudaMemsetAsync(ctx->d_state, 0, sizeof(IcpState), ctx->stream));
+    {
+        const int rc = ensure_trials(ctx, 1);
+        if (rc) return rc;
+    }
+    CK(cudaMalloc(&ctx->d_n_active, sizeof(unsigned int)));
+    CK(cudaMemsetAsync(ctx->d_n_active, 0, sizeof(unsigned int), ctx->stream));
     CK(cudaMalloc(&ctx->d_small, 1024 * sizeof(double)));
     if (!getenv("DCREG_NO_K2_REHEARSAL")) {
         CK(cudaMalloc(&ctx->d_k2_scratch, sizeof(K2Scratch)));
@@ -881,9 +997,10 @@ int dcreg_create(int device_id, dcreg_ctx** out) {
 int dcreg_destroy(dcreg_ctx* ctx) {
     if (!ctx) return DCREG_BAD_ARG;
     cudaSetDevice(ctx->device);
-    if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    void* ptrs[] = {ctx->d_src, ctx->d_stage, ctx->d_tgt, ctx->grid.keys, ctx->grid.cell_start, ctx->grid.hstart,
+    dcreg_comm_destroy(ctx);
+    if (ctx->graph_exec) cudaGraphExecDestroy(ctx->graph_exec);
+    void* ptrs[] = {ctx->d_n_active, ctx->d_T_init, ctx->d_sort_tmp, ctx->d_src, ctx->d_stage, ctx->d_tgt, ctx->grid.keys, ctx->grid.cell_start, ctx->grid.hstart,
                     ctx->grid.hcount, ctx->d_src_sorted, ctx->d_cell_tmp, ctx->d_pt_cell, ctx->d_tile_sums,
                     ctx->grid.pts, ctx->d_planes64, ctx->d_planes32, ctx->d_partials, ctx->d_counter, ctx->d_acc,
                     ctx->d_state, ctx->d_log, ctx->d_small, ctx->d_analysis, ctx->d_flush, ctx->d_nn, ctx->d_plane_cache, ctx->d_fit_state, ctx->d_iter_stats, ctx->d_src_radius, ctx->d_plane_key, ctx->d_k2_scratch};
@@ -972,6 +1089,7 @@ static int build_grid(dcreg_ctx* ctx, const float4* d_pts, long long m, double c
     const long long ncells = nx * ny * nz;
     const unsigned nb = (unsigned)((m + 255) / 256);
     int *pt_cell = nullptr, *fill = nullptr, *counts = nullptr;
+    float4* tmp_pts = nullptr;                      // points grouped by cell in arrival order, before the in-cell ranking
     CK(cudaMalloc(&pt_cell, (size_t)m * sizeof(int)));
     cudaError_t e = cudaSuccess;
     int rc = DCREG_OK;
@@ -985,9 +1103,9 @@ static int build_grid(dcreg_ctx* ctx, const float4* d_pts, long long m, double c
         CK(cudaMemsetAsync(fill, 0, (size_t)ncells * sizeof(int), ctx->stream));
         corr::grid_count_dense_kernel<<<nb, 256, 0, ctx->stream>>>(d_pts, (int)m, g, pt_cell, counts);
         rc = device_exclusive_scan(ctx, counts, ncells + 1, g.cell_start);
-        corr::grid_scatter_kernel<<<nb, 256, 0, ctx->stream>>>(d_pts, (int)m, pt_cell, g.cell_start, fill, g.pts, 0);
-        corr::grid_sort_cells_kernel<<<(unsigned)((ncells + 255) / 256), 256, 0, ctx->stream>>>(g.pts, g.cell_start, nullptr,
-                                                                                               g.cell_start + 1, ncells);
+        CK(cudaMalloc(&tmp_pts, (size_t)m * sizeof(float4)));
+        corr::grid_scatter_kernel<<<nb, 256, 0, ctx->stream>>>(d_pts, (int)m, pt_cell, g.cell_start, fill, tmp_pts, 0);
+        corr::grid_rank_cells_kernel<<<nb, 256, 0, ctx->stream>>>(tmp_pts, (int)m, pt_cell, g.cell_start, nullptr, g.pts);
         ctx->launches += 3;
         e = cudaStreamSynchronize(ctx->stream);
     } else {
@@ -1004,12 +1122,14 @@ static int build_grid(dcreg_ctx* ctx, const float4* d_pts, long long m, double c
         CK(cudaMemsetAsync(fill, 0, (size_t)cap * sizeof(int), ctx->stream));
         corr::grid_insert_hash_kernel<<<nb, 256, 0, ctx->stream>>>(d_pts, (int)m, g, pt_cell);
         rc = device_exclusive_scan(ctx, g.hcount, cap, g.hstart);
-        corr::grid_scatter_kernel<<<nb, 256, 0, ctx->stream>>>(d_pts, (int)m, pt_cell, g.hstart, fill, g.pts, 0);
-        corr::grid_sort_cells_kernel<<<(cap + 255) / 256, 256, 0, ctx->stream>>>(g.pts, g.hstart, g.hcount, nullptr, cap);
+        CK(cudaMalloc(&tmp_pts, (size_t)m * sizeof(float4)));
+        corr::grid_scatter_kernel<<<nb, 256, 0, ctx->stream>>>(d_pts, (int)m, pt_cell, g.hstart, fill, tmp_pts, 0);
+        corr::grid_rank_cells_kernel<<<nb, 256, 0, ctx->stream>>>(tmp_pts, (int)m, pt_cell, g.hstart, g.hcount, g.pts);
         ctx->launches += 3;
         e = cudaStreamSynchronize(ctx->stream);
     }
     cudaFree(pt_cell); cudaFree(fill);
+    if (tmp_pts) cudaFree(tmp_pts);
     if (counts) cudaFree(counts);
     if (rc) { free_grid(&g); return rc; }
     if (e != cudaSuccess) { free_grid(&g); ctx->err = std::string("grid build: ") + cudaGetErrorString(e); return DCREG_CUDA_ERROR; }
@@ -1099,9 +1219,11 @@ static int sort_source_by_cell(dcreg_ctx* ctx, const double T[16], const float4*
     const long long n = ctx->n_src, ncells = ctx->grid_cells;
     if (ctx->src_sorted_cap < n) {
         if (ctx->d_src_sorted) cudaFree(ctx->d_src_sorted);
+        if (ctx->d_sort_tmp) cudaFree(ctx->d_sort_tmp);
         if (ctx->d_pt_cell) cudaFree(ctx->d_pt_cell);
-        ctx->d_src_sorted = nullptr; ctx->d_pt_cell = nullptr; ctx->src_sorted_cap = 0;
+        ctx->d_src_sorted = nullptr; ctx->d_sort_tmp = nullptr; ctx->d_pt_cell = nullptr; ctx->src_sorted_cap = 0;
         CK(cudaMalloc(&ctx->d_src_sorted, (size_t)n * sizeof(float4)));
+        CK(cudaMalloc(&ctx->d_sort_tmp, (size_t)n * sizeof(float4)));
         CK(cudaMalloc(&ctx->d_pt_cell, (size_t)n * sizeof(int)));
         ctx->src_sorted_cap = n;
     }
@@ -1122,9 +1244,8 @@ static int sort_source_by_cell(dcreg_ctx* ctx, const double T[16], const float4*
     corr::source_cell_kernel<<<nb, 256, 0, ctx->stream>>>(ctx->d_src, (int)n, ctx->grid, dT, ctx->d_pt_cell, counts);
     int rc = device_exclusive_scan(ctx, counts, ncells + 1, start);
     if (rc) return rc;
-    corr::grid_scatter_kernel<<<nb, 256, 0, ctx->stream>>>(ctx->d_src, (int)n, ctx->d_pt_cell, start, fill, ctx->d_src_sorted, 0);
-    corr::grid_sort_cells_kernel<<<(unsigned)((ncells + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_src_sorted, start, nullptr,
-                                                                                           start + 1, ncells);
+    corr::grid_scatter_kernel<<<nb, 256, 0, ctx->stream>>>(ctx->d_src, (int)n, ctx->d_pt_cell, start, fill, ctx->d_sort_tmp, 0);
+    corr::grid_rank_cells_kernel<<<nb, 256, 0, ctx->stream>>>(ctx->d_sort_tmp, (int)n, ctx->d_pt_cell, start, nullptr, ctx->d_src_sorted);
     ctx->launches += 3;
     CK(cudaGetLastError());
     *src_out = ctx->d_src_sorted;
@@ -1137,13 +1258,23 @@ static double coherent_step_setting() {
     return v;
 }
 
-static int launch_iteration(dcreg_ctx* ctx, const dcreg_icp_params* prm, const float4* src, double4* planes_out) {
-    const int grid = stream_grid(ctx, ctx->n_src, 16);
-    int rc = ensure_partials(ctx, grid);
-    if (rc) return rc;
-    IterArgs a{};
+// What one loop body looks like for this context: which kernel, its grid, and whether the solve step is inside it.
+struct LoopPlan {
+    bool fused2 = false;      // icp_iter2_kernel (dense grid): records, work lists, in-kernel solve step
+    bool fold_k2 = false;     // the solve / update step runs in the iteration kernel's last block
+    int grid_x = 1, trials = 1;
+    Iter2Args b{};            // arguments of the fused2 kernel
+    IterArgs a{};             // arguments of the one-thread-per-slot kernel (hash grids, seam 1)
+    bool use_wd = false;
+};
+
+static int plan_iteration(dcreg_ctx* ctx, const dcreg_icp_params* prm, const float4* src, double4* planes_out, int trials,
+                          dcreg_iter_log* dlog, int log_cap, bool want_fold, LoopPlan* plan) {
+    LoopPlan& L = *plan;
+    L.trials = trials; L.use_wd = prm->use_weight_derivative != 0;
+    IterArgs& a = L.a;
     a.src = src; a.n = ctx->n_src; a.grid = ctx->grid; a.state = ctx->d_state;
-    a.partials = ctx->d_partials; a.counter = ctx->d_counter; a.acc = ctx->d_acc;
+    a.counter = ctx->d_counter; a.acc = ctx->d_acc;
     a.planes_out = planes_out; a.prm = *prm;
     {   // rings of cells that cover the search radius (exactness of the 5-NN-within-radius rule)
         const int rings = (int)ceil(prm->search_radius / ctx->cell_size - 1e-9);
@@ -1153,23 +1284,36 @@ static int launch_iteration(dcreg_ctx* ctx, const dcreg_icp_params* prm, const f
         }
         a.grid.rings = rings;
     }
-    const bool fused2 = ctx->grid.dense && !planes_out && ctx->n_src <= 0x1fffffffLL && !getenv("DCREG_FUSED_SEARCH");
-    if (fused2) {
-        if (ctx->nn_cap < ctx->n_src) {
-            if (ctx->d_nn) cudaFree(ctx->d_nn);
-            if (ctx->d_plane_cache) cudaFree(ctx->d_plane_cache);
-            if (ctx->d_fit_state) cudaFree(ctx->d_fit_state);
-            ctx->d_nn = nullptr; ctx->d_plane_cache = nullptr; ctx->d_fit_state = nullptr; ctx->nn_cap = 0;
-            CK(cudaMalloc(&ctx->d_nn, (size_t)ctx->n_src * kNnRec * sizeof(int4)));
-            CK(cudaMalloc(&ctx->d_plane_cache, (size_t)ctx->n_src * sizeof(double4)));
-            CK(cudaMalloc(&ctx->d_fit_state, (size_t)ctx->n_src));
-            if (ctx->d_plane_key) cudaFree(ctx->d_plane_key);
-            ctx->d_plane_key = nullptr;
-            CK(cudaMalloc(&ctx->d_plane_key, (size_t)ctx->n_src * 5 * sizeof(int)));
-            ctx->nn_cap = ctx->n_src;
+    L.fused2 = ctx->grid.dense && !planes_out && ctx->n_src <= 0x1fffffffLL && !getenv("DCREG_FUSED_SEARCH");
+    if (trials > 1 && !L.fused2) {
+        ctx->err = "batched trials need the dense target grid (target bounding box / cell size too large for it)";
+        return DCREG_BAD_ARG;
+    }
+    if (L.fused2) {
+        const long long slots = ctx->n_src;
+        if (ctx->nn_cap < slots || ctx->nn_trials < trials) {
+            void* old[] = {ctx->d_nn, ctx->d_plane_cache, ctx->d_fit_state, ctx->d_plane_key};
+            for (void* p : old)
+                if (p) cudaFree(p);
+            ctx->d_nn = nullptr; ctx->d_plane_cache = nullptr; ctx->d_fit_state = nullptr; ctx->d_plane_key = nullptr;
+            ctx->nn_cap = 0; ctx->nn_trials = 0;
+            const size_t tot = (size_t)slots * (size_t)trials;
+            CK(cudaMalloc(&ctx->d_nn, tot * kNnRec * sizeof(int4)));
+            CK(cudaMalloc(&ctx->d_plane_cache, tot * sizeof(double4)));
+            CK(cudaMalloc(&ctx->d_fit_state, tot));
+            CK(cudaMalloc(&ctx->d_plane_key, tot * 5 * sizeof(int)));
+            ctx->nn_cap = slots; ctx->nn_trials = trials;
             ctx->nn_valid = false;
         }
-        Iter2Args b{};
+        // blocks per trial: one 256-slot tile per block while the whole launch fits the resident slots (3 per SM)
+        long long gx = (slots + kBlock - 1) / kBlock;
+        if (trials == 1) { const long long cap = (long long)ctx->sm_count * 3; if (gx > cap) gx = cap; }
+        else if (gx > 64) gx = 64;
+        L.grid_x = (int)gx;
+        int rc = ensure_partials(ctx, L.grid_x * trials);
+        if (rc) return rc;
+        a.partials = ctx->d_partials;
+        Iter2Args& b = L.b;
         b.it = a;
         b.nn = ctx->d_nn; b.plane_cache = ctx->d_plane_cache; b.fit_state = ctx->d_fit_state; b.plane_key = ctx->d_plane_key;
         b.force = ctx->force_coherent ? 1 : 0;
@@ -1181,31 +1325,75 @@ static int launch_iteration(dcreg_ctx* ctx, const dcreg_icp_params* prm, const f
         float r2f = (float)r2;
         if ((double)r2f < r2) r2f = nextafterf(r2f, INFINITY);
         b.r2_up = r2f;
-        ctx->nn_valid = true;
-        const int g2 = stream_grid(ctx, ctx->n_src, 3);
-        static bool configured = false;
-        if (!configured) {
+        // the solve step inside the kernel unless the sum over ranks has to go through NCCL
+        L.fold_k2 = want_fold && !(ctx->comm && !ctx->peer_ok) && !getenv("DCREG_NO_FOLD") &&
+                    prm->detection == DCREG_DET_SCHUR_CONDITION_NUMBER && prm->handling == DCREG_HAND_PRECONDITIONED_CG;
+        b.fold_k2 = L.fold_k2 ? 1 : 0;
+        b.log = dlog; b.log_cap = log_cap;
+        b.src_radius = ctx->d_src_radius; b.coherent_step = coherent_step_setting();
+        b.n_active = ctx->d_n_active;
+        if (ctx->peer_ok) b.peer = ctx->peer_view;
+        if (!ctx->loop_attr_done) {          // per device (= per context), not per process
             CK(cudaFuncSetAttribute(icp_iter2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Iter2Smem)));
             CK(cudaFuncSetAttribute(icp_iter2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Iter2Smem)));
             CK(cudaFuncSetAttribute(icp_iter2_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
             CK(cudaFuncSetAttribute(icp_iter2_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-            configured = true;
+            ctx->loop_attr_done = true;
         }
-        if (prm->use_weight_derivative) CK(launch_pdl(icp_iter2_kernel<true>, dim3(g2), dim3(kBlock), sizeof(Iter2Smem), ctx->stream, b));
-        else CK(launch_pdl(icp_iter2_kernel<false>, dim3(g2), dim3(kBlock), sizeof(Iter2Smem), ctx->stream, b));
     } else {
-        if (prm->use_weight_derivative) icp_iteration_kernel<true><<<grid, kBlock, 0, ctx->stream>>>(a);
-        else icp_iteration_kernel<false><<<grid, kBlock, 0, ctx->stream>>>(a);
+        L.grid_x = stream_grid(ctx, ctx->n_src, 16);
+        int rc = ensure_partials(ctx, L.grid_x);
+        if (rc) return rc;
+        a.partials = ctx->d_partials;
+        L.fold_k2 = false;
+    }
+    return DCREG_OK;
+}
+
+// enqueue the iteration kernel of a plan (inside or outside a stream capture)
+static int launch_plan(dcreg_ctx* ctx, LoopPlan& L) {
+    if (L.fused2) {
+        L.b.use_seeds = ctx->nn_valid ? 1 : 0;
+        ctx->nn_valid = true;
+        const dim3 grid((unsigned)L.grid_x, (unsigned)L.trials);
+        if (L.use_wd) CK(launch_pdl(icp_iter2_kernel<true>, grid, dim3(kBlock), sizeof(Iter2Smem), ctx->stream, L.b));
+        else CK(launch_pdl(icp_iter2_kernel<false>, grid, dim3(kBlock), sizeof(Iter2Smem), ctx->stream, L.b));
+    } else {
+        if (L.use_wd) icp_iteration_kernel<true><<<L.grid_x, kBlock, 0, ctx->stream>>>(L.a);
+        else icp_iteration_kernel<false><<<L.grid_x, kBlock, 0, ctx->stream>>>(L.a);
     }
     ctx->launches++;
     CK(cudaGetLastError());
     return DCREG_OK;
 }
 
-static int init_state(dcreg_ctx* ctx, const double T[16]) {
+// the separate solve kernel (one warp per trial): baseline methods, hash-grid / seam paths, NCCL fallback of a sharded run
+static int launch_k2(dcreg_ctx* ctx, const dcreg_icp_params* prm, dcreg_iter_log* dlog, int log_cap, int trials = 1) {
+    CK(launch_pdl(k2_step_kernel, dim3((unsigned)trials), dim3(32), 0, ctx->stream, (const double*)ctx->d_acc, ctx->d_state, *prm,
+                  dlog, log_cap, (const float*)ctx->d_src_radius, coherent_step_setting(),
+                  trials == 1 ? ctx->d_k2_scratch : (K2Scratch*)nullptr, ctx->d_n_active));
+    ctx->launches++;
+    return DCREG_OK;
+}
+
+// one loop body: iteration kernel [+ all-reduce + solve kernel when the step is not folded]
+static int launch_body(dcreg_ctx* ctx, LoopPlan& L, const dcreg_icp_params* prm, dcreg_iter_log* dlog, int log_cap, bool with_k2) {
+    int rc = launch_plan(ctx, L);
+    if (rc) return rc;
+    if (with_k2 && !L.fold_k2) {
+        if ((rc = nccl_allreduce_acc(ctx))) return rc;          // no-op on one GPU / with peer mailboxes
+        if ((rc = launch_k2(ctx, prm, dlog, log_cap, L.trials))) return rc;
+    }
+    return DCREG_OK;
+}
+
+static int init_state(dcreg_ctx* ctx, const double* T, int trials = 1) {
     ctx->nn_valid = false;            // a new run: no neighbours of a previous iteration to seed the search with
-    CK(cudaMemcpyAsync(ctx->d_small, T, 16 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    init_state_kernel<<<1, 32, 0, ctx->stream>>>(ctx->d_state, ctx->d_small, ctx->n_src_total, ctx->d_counter);
+    int rc = ensure_trials(ctx, trials);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(ctx->d_T_init, T, (size_t)trials * 16 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    init_state_kernel<<<(trials + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_state, ctx->d_T_init, ctx->n_src_total, ctx->d_counter,
+                                                                   trials, ctx->d_n_active);
     ctx->launches++;
     CK(cudaGetLastError());
     return DCREG_OK;
@@ -1223,7 +1411,9 @@ int dcreg_find_planes(dcreg_ctx* ctx, const double T[16], double search_radius, 
     prm.search_radius = search_radius;
     prm.min_effective_points = 0;
     if ((rc = init_state(ctx, T))) return rc;
-    if ((rc = launch_iteration(ctx, &prm, ctx->d_src, ctx->d_planes64))) return rc;
+    LoopPlan L;
+    if ((rc = plan_iteration(ctx, &prm, ctx->d_src, ctx->d_planes64, 1, nullptr, 0, false, &L))) return rc;
+    if ((rc = launch_plan(ctx, L))) return rc;
     double acc[kAcc];
     CK(cudaMemcpyAsync(acc, ctx->d_acc, sizeof(acc), cudaMemcpyDeviceToHost, ctx->stream));
     if (planes_out)
@@ -1375,20 +1565,17 @@ int dcreg_time_iteration(dcreg_ctx* ctx, const dcreg_icp_params* params, const d
     const float4* src_iter = ctx->d_src;
     if ((rc = sort_source_by_cell(ctx, T, &src_iter))) return rc;
     ctx->force_coherent = (what == 0);                                     // fixed pose: measure the record-reusing mode
+    LoopPlan L;
+    rc = plan_iteration(ctx, &prm, src_iter, nullptr, 1, nullptr, 0, what == 1, &L);
+    ctx->force_coherent = false;
+    if (rc) return rc;
     for (int warm = 0; warm < 2; ++warm)                                   // instruction caches, lazy module load
-        if ((rc = launch_iteration(ctx, &prm, src_iter, nullptr))) { ctx->force_coherent = false; return rc; }
+        if ((rc = launch_body(ctx, L, &prm, nullptr, 0, false))) return rc;
     cudaEvent_t b0, b1;
     CK(cudaEventCreate(&b0)); CK(cudaEventCreate(&b1));
     CK(cudaEventRecord(b0, ctx->stream));
-    for (int i = 0; i < reps; ++i) {
-        if ((rc = launch_iteration(ctx, &prm, src_iter, nullptr))) return rc;
-        if (what == 1) {
-            if ((rc = nccl_allreduce_acc(ctx))) return rc;
-            CK(launch_pdl(k2_step_kernel, dim3(1), dim3(32), 0, ctx->stream, (const double*)ctx->d_acc, ctx->d_state, prm, (dcreg_iter_log*)nullptr, 0, (const float*)ctx->d_src_radius, coherent_step_setting(), ctx->d_k2_scratch));
-            ctx->launches++;
-        }
-    }
-    ctx->force_coherent = false;
+    for (int i = 0; i < reps; ++i)
+        if ((rc = launch_body(ctx, L, &prm, nullptr, 0, what == 1))) return rc;
     CK(cudaEventRecord(b1, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     float ms = 0.f;
@@ -1435,49 +1622,138 @@ int dcreg_solve_pcg(dcreg_ctx* ctx, const double A[36], const double b[6], const
     return DCREG_OK;
 }
 
+// FNV-1a over the bytes that define a captured chunk of the loop
+static void key_bytes(std::vector<unsigned char>& k, const void* p, size_t n) {
+    const unsigned char* c = (const unsigned char*)p;
+    k.insert(k.end(), c, c + n);
+}
+
+// Enqueue `iters` loop bodies.  The bodies are identical launches (pose, mode flags and the done flag live on the
+// device), so a chunk is captured once into a CUDA graph and replayed: one host call per chunk instead of one or two
+// launches per iteration - what keeps 8 independent ranks from queueing behind the host (round 1: 0.887 weak scaling
+// at 8 GPUs with nothing shared between the ranks).  Falls back to plain launches if capture is unavailable.
+static int enqueue_iterations(dcreg_ctx* ctx, LoopPlan& L, const dcreg_icp_params* prm, dcreg_iter_log* dlog, int log_cap, int iters) {
+    static int use_graph = -1;
+    if (use_graph < 0) use_graph = getenv("DCREG_NO_GRAPH") ? 0 : 1;
+    const bool graphable = use_graph && !ctx->graph_off && L.fused2 && !L.b.force && iters > 1 &&
+                           (L.fold_k2 || !(ctx->comm && !ctx->peer_ok));          // no NCCL call inside a capture
+    if (graphable) {
+        std::vector<unsigned char> key;
+        Iter2Args kb = L.b;
+        kb.use_seeds = 0;
+        key_bytes(key, &kb, sizeof(kb));
+        const int meta[4] = {L.grid_x, L.trials, L.use_wd ? 1 : 0, iters};
+        key_bytes(key, meta, sizeof(meta));
+        key_bytes(key, prm, sizeof(*prm));
+        if (!ctx->graph_exec || key != ctx->graph_key) {
+            if (ctx->graph_exec) { cudaGraphExecDestroy(ctx->graph_exec); ctx->graph_exec = nullptr; }
+            ctx->graph_key.clear();
+            cudaGraph_t graph = nullptr;
+            const bool nn_valid0 = ctx->nn_valid;
+            const long long launches0 = ctx->launches;
+            cudaError_t e = cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed);
+            int rc = DCREG_OK;
+            if (e == cudaSuccess) {
+                for (int k = 0; k < iters && rc == DCREG_OK; ++k) rc = launch_body(ctx, L, prm, dlog, log_cap, true);
+                e = cudaStreamEndCapture(ctx->stream, &graph);
+            }
+            ctx->nn_valid = nn_valid0; ctx->launches = launches0;      // nothing has run yet
+            if (e == cudaSuccess && rc == DCREG_OK && graph) e = cudaGraphInstantiate(&ctx->graph_exec, graph, 0);
+            if (graph) cudaGraphDestroy(graph);
+            if (e != cudaSuccess || rc != DCREG_OK || !ctx->graph_exec) {
+                cudaGetLastError();                                    // clear; run without a graph from now on
+                ctx->graph_exec = nullptr; ctx->graph_off = true;
+            } else {
+                ctx->graph_key = key;
+            }
+        }
+        if (ctx->graph_exec) {
+            CK(cudaGraphLaunch(ctx->graph_exec, ctx->stream));
+            ctx->nn_valid = true;
+            ctx->launches += (long long)iters * (L.fold_k2 ? 1 : 2); ctx->graph_launches++;
+            return DCREG_OK;
+        }
+    }
+    for (int k = 0; k < iters; ++k) {
+        const int rc = launch_body(ctx, L, prm, dlog, log_cap, true);
+        if (rc) return rc;
+    }
+    return DCREG_OK;
+}
+
+// The loop for `trials` registrations of the context's source against its target, side by side.
+static int run_loop(dcreg_ctx* ctx, const dcreg_icp_params* params, int trials, const double* T_init, double* T_out,
+                    dcreg_iter_log* log, int log_cap, int* n_iterations, int* converged, int* status) {
+    int rc;
+    if (log && log_cap > 0 && (rc = ensure_log(ctx, (long long)trials * log_cap))) return rc;
+    dcreg_iter_log* dlog = (log && log_cap > 0) ? ctx->d_log : nullptr;
+    if (dlog) CK(cudaMemsetAsync(dlog, 0, (size_t)trials * log_cap * sizeof(dcreg_iter_log), ctx->stream));   // aborted iterations leave fields untouched
+    if ((rc = init_state(ctx, T_init, trials))) return rc;
+    const float4* src_iter = ctx->d_src;
+    if ((rc = sort_source_by_cell(ctx, T_init, &src_iter))) return rc;       // locality only: any pose of the batch will do
+    LoopPlan L;
+    if ((rc = plan_iteration(ctx, params, src_iter, nullptr, trials, dlog, dlog ? log_cap : 0, true, &L))) return rc;
+    if ((rc = ensure_pinned(ctx, (size_t)trials * sizeof(IcpState)))) return rc;
+    // fixed iteration count: the whole run is one chunk; otherwise chunks of 16 with a peek at the number of running
+    // trials in between (the only host sync inside a run; iterations past convergence exit at once on the device)
+    const int chunk = params->fixed_iterations ? (params->max_iterations < 64 ? params->max_iterations : 64) : 16;
+    int issued = 0;
+    while (issued < params->max_iterations) {
+        int todo = params->max_iterations - issued;
+        if (todo > chunk) todo = chunk;
+        // a captured chunk is always `chunk` bodies long (one graph per run shape); bodies past max_iterations exit at once
+        const int bodies = (todo < chunk && issued > 0) ? chunk : todo;
+        if ((rc = enqueue_iterations(ctx, L, params, dlog, dlog ? log_cap : 0, bodies))) return rc;
+        issued += bodies;
+        if (issued < params->max_iterations && !params->fixed_iterations) {
+            unsigned int* flag = (unsigned int*)ctx->h_pinned;
+            if (L.fold_k2) CK(cudaMemcpyAsync(flag, ctx->d_n_active, sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
+            else CK(cudaMemcpyAsync(flag, &ctx->d_state->done, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            if (L.fold_k2 ? (*flag == 0u) : (*flag != 0u)) break;
+        }
+    }
+    if (dlog) {
+        log_fill_kernel<<<dim3((log_cap + 31) / 32, trials), 32, 0, ctx->stream>>>(dlog, log_cap, ctx->d_state, *params);
+        ctx->launches++;
+    }
+    return read_results(ctx, trials, T_out, log, log_cap, n_iterations, converged, status);
+}
+
+static int check_run_args(dcreg_ctx* ctx, const dcreg_icp_params* params) {
+    if (!ctx->d_src || ctx->n_src <= 0) { ctx->err = "[ICP Error] Input measure cloud is null or empty."; return DCREG_BAD_ARG; }
+    if (!ctx->has_grid) { ctx->err = "[ICP Error] Target index is not set up in context."; return DCREG_BAD_ARG; }
+    if (params->max_iterations < 0) { ctx->err = "icp_run: max_iterations < 0"; return DCREG_BAD_ARG; }
+    if (!(params->weight_slope > 0.0) || !(params->weight_gate >= 0.0) || !(params->weight_gate < 1.0)) {
+        ctx->err = "icp_run: weight_slope must be > 0 and weight_gate in [0, 1)";
+        return DCREG_BAD_ARG;
+    }
+    return DCREG_OK;
+}
+
 int dcreg_icp_run(dcreg_ctx* ctx, const dcreg_icp_params* params, const double T_init[16], double T_out[16],
                   dcreg_iter_log* log, int log_cap, int* n_iterations, int* converged) {
     if (!ctx) return DCREG_BAD_ARG;
     if (!params || !T_init || !T_out) { ctx->err = "icp_run: null pointer"; return DCREG_BAD_ARG; }
-    if (!ctx->d_src || ctx->n_src <= 0) { ctx->err = "[ICP Error] Input measure cloud is null or empty."; return DCREG_BAD_ARG; }
-    if (!ctx->has_grid) { ctx->err = "[ICP Error] Target index is not set up in context."; return DCREG_BAD_ARG; }
-    if (params->max_iterations < 0) { ctx->err = "icp_run: max_iterations < 0"; return DCREG_BAD_ARG; }
+    int rc = check_run_args(ctx, params);
+    if (rc) return rc;
     CK(cudaSetDevice(ctx->device));
-    int rc;
-    if (log && log_cap > 0 && (rc = ensure_log(ctx, log_cap))) return rc;
-    dcreg_iter_log* dlog = (log && log_cap > 0) ? ctx->d_log : nullptr;
-    if ((rc = init_state(ctx, T_init))) return rc;
-    const float4* src_iter = ctx->d_src;
-    if ((rc = sort_source_by_cell(ctx, T_init, &src_iter))) return rc;
-    int issued = 0;
-    int chunk = 16;
     int status = DCREG_OK;
-    int rc2 = ensure_pinned(ctx, sizeof(IcpState));
-    if (rc2) return rc2;
-    while (issued < params->max_iterations) {
-        const int todo = (params->max_iterations - issued) < chunk ? (params->max_iterations - issued) : chunk;
-        for (int k = 0; k < todo; ++k) {
-            if ((rc = launch_iteration(ctx, params, src_iter, nullptr))) return rc;
-            if ((rc = nccl_allreduce_acc(ctx))) return rc;          // no-op on one GPU
-            CK(launch_pdl(k2_step_kernel, dim3(1), dim3(32), 0, ctx->stream, (const double*)ctx->d_acc, ctx->d_state, *params, dlog, log_cap, (const float*)ctx->d_src_radius, coherent_step_setting(), ctx->d_k2_scratch));
-            ctx->launches++;
-        }
-        issued += todo;
-        if (issued < params->max_iterations && !params->fixed_iterations) {
-            // peek at the done flag between chunks (the only host sync inside a run)
-            int* flag = (int*)ctx->h_pinned;
-            CK(cudaMemcpyAsync(flag, &ctx->d_state->done, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-            CK(cudaStreamSynchronize(ctx->stream));
-            if (*flag) break;
-            chunk = 32;
-        }
-    }
-    if (dlog) {
-        log_fill_kernel<<<(log_cap + 31) / 32, 32, 0, ctx->stream>>>(dlog, log_cap, ctx->d_state, *params);
-        ctx->launches++;
-    }
-    if ((rc = read_results(ctx, T_out, log, log_cap, n_iterations, converged, &status))) return rc;
+    if ((rc = run_loop(ctx, params, 1, T_init, T_out, log, log_cap, n_iterations, converged, &status))) return rc;
     return status;
+}
+
+int dcreg_icp_run_batch(dcreg_ctx* ctx, const dcreg_icp_params* params, int n_trials, const double* T_init,
+                        double* T_out, int* n_iterations, int* converged, int* status, dcreg_iter_log* log, int log_cap) {
+    if (!ctx) return DCREG_BAD_ARG;
+    if (!params || !T_init || !T_out || n_trials <= 0) { ctx->err = "icp_run_batch: null pointer or n_trials <= 0"; return DCREG_BAD_ARG; }
+    if (ctx->comm) { ctx->err = "icp_run_batch: trials are independent - distribute them over ranks, do not shard them"; return DCREG_BAD_ARG; }
+    int rc = check_run_args(ctx, params);
+    if (rc) return rc;
+    CK(cudaSetDevice(ctx->device));
+    std::vector<int> st_local;
+    if (!status) { st_local.resize(n_trials); status = st_local.data(); }
+    return run_loop(ctx, params, n_trials, T_init, T_out, log, log_cap, n_iterations, converged, status);
 }
 
 int dcreg_icp_run_host_planes(dcreg_ctx* ctx, const dcreg_icp_params* params, const double T_init[16],
@@ -1490,6 +1766,7 @@ int dcreg_icp_run_host_planes(dcreg_ctx* ctx, const dcreg_icp_params* params, co
     int rc;
     if (log && log_cap > 0 && (rc = ensure_log(ctx, log_cap))) return rc;
     dcreg_iter_log* dlog = (log && log_cap > 0) ? ctx->d_log : nullptr;
+    if (dlog) CK(cudaMemsetAsync(dlog, 0, (size_t)log_cap * sizeof(dcreg_iter_log), ctx->stream));
     if ((rc = ensure_planes(ctx, ctx->n_src))) return rc;
     if ((rc = ensure_pinned(ctx, sizeof(IcpState) + (size_t)ctx->n_src * sizeof(double4)))) return rc;
     IcpState* hs = (IcpState*)ctx->h_pinned;
@@ -1498,7 +1775,7 @@ int dcreg_icp_run_host_planes(dcreg_ctx* ctx, const dcreg_icp_params* params, co
     double T[16];
     memcpy(T, T_init, sizeof(T));
     for (int it = 0; it < params->max_iterations; ++it) {
-        int64_t npt = 0;
+        int64_t npt = -1;
         if (cb(user, T, hplanes, &npt) != 0) { ctx->err = "plane callback failed"; return DCREG_BAD_ARG; }
         CK(cudaMemcpyAsync(ctx->d_planes64, hplanes, (size_t)ctx->n_src * sizeof(double4), cudaMemcpyHostToDevice,
                            ctx->stream));
@@ -1507,11 +1784,13 @@ int dcreg_icp_run_host_planes(dcreg_ctx* ctx, const dcreg_icp_params* params, co
             for (int c = 0; c < 3; ++c) P.R[r * 3 + c] = T[r * 4 + c];
             P.t[r] = T[r * 4 + 3];
         }
-        if ((rc = launch_reduce(ctx, ctx->d_src, ctx->d_planes64, true, ctx->n_src, &P, params->use_weight_derivative)))
+        // n_corr_pt is the caller's count (5th neighbour inside the radius, BEFORE the plane gates:
+        // icp_test_runner.cpp:1726-1731, 1856), not the number of non-zero planes K1 sees
+        if ((rc = launch_reduce(ctx, ctx->d_src, ctx->d_planes64, true, ctx->n_src, &P, params->use_weight_derivative,
+                                params->weight_slope, params->weight_gate, npt >= 0 ? (double)npt : -1.0)))
             return rc;
         if ((rc = nccl_allreduce_acc(ctx))) return rc;
-        CK(launch_pdl(k2_step_kernel, dim3(1), dim3(32), 0, ctx->stream, (const double*)ctx->d_acc, ctx->d_state, *params, dlog, log_cap, (const float*)ctx->d_src_radius, coherent_step_setting(), ctx->d_k2_scratch));
-        ctx->launches++;
+        if ((rc = launch_k2(ctx, params, dlog, log_cap))) return rc;
         CK(cudaMemcpyAsync(hs, ctx->d_state, sizeof(IcpState), cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
         for (int r = 0; r < 3; ++r) {
@@ -1522,10 +1801,10 @@ int dcreg_icp_run_host_planes(dcreg_ctx* ctx, const dcreg_icp_params* params, co
     }
     int status = DCREG_OK;
     if (dlog) {
-        log_fill_kernel<<<(log_cap + 31) / 32, 32, 0, ctx->stream>>>(dlog, log_cap, ctx->d_state, *params);
+        log_fill_kernel<<<dim3((log_cap + 31) / 32, 1), 32, 0, ctx->stream>>>(dlog, log_cap, ctx->d_state, *params);
         ctx->launches++;
     }
-    if ((rc = read_results(ctx, T_out, log, log_cap, n_iterations, converged, &status))) return rc;
+    if ((rc = read_results(ctx, 1, T_out, log, log_cap, n_iterations, converged, &status))) return rc;
     return status;
 }
 
@@ -1550,6 +1829,72 @@ int dcreg_comm_unique_id(dcreg_ctx* ctx, uint8_t id_out[128]) {
     return DCREG_OK;
 }
 
+// Map every rank's mailbox into this process (cudaIpc handles carried by one ncclAllGather): afterwards the sum over
+// ranks runs inside the reducing kernels (peer_reduce.cuh) and NCCL is not on the data path any more.  Any failure
+// leaves peer_ok = false: the NCCL all-reduce fallback stays in place.
+static void setup_peer_mailboxes(dcreg_ctx* ctx) {
+    ctx->peer_ok = false;
+    if (ctx->nranks < 2 || ctx->nranks > peer::kMaxRanks || !g_nccl.AllGather || getenv("DCREG_NO_PEER")) return;
+    cudaIpcMemHandle_t mine;
+    unsigned char* d_handles = nullptr;
+    std::vector<cudaIpcMemHandle_t> all(ctx->nranks);
+    bool ok = cudaMalloc(&ctx->d_mailbox, sizeof(peer::Mailbox)) == cudaSuccess &&
+              cudaMemset(ctx->d_mailbox, 0, sizeof(peer::Mailbox)) == cudaSuccess &&
+              cudaIpcGetMemHandle(&mine, ctx->d_mailbox) == cudaSuccess &&
+              cudaMalloc(&d_handles, sizeof(mine) * ctx->nranks) == cudaSuccess;
+    // every rank takes part in the collectives below even if its own setup failed (flag travels with the handle)
+    unsigned char blob[sizeof(cudaIpcMemHandle_t)];
+    memset(blob, 0, sizeof(blob));
+    if (ok) memcpy(blob, &mine, sizeof(mine));
+    unsigned char* d_mine = nullptr;
+    if (cudaMalloc(&d_mine, sizeof(blob)) != cudaSuccess) { ok = false; }
+    if (!d_handles || !d_mine) {          // cannot even run the collective coherently: give up on every rank the same way
+        if (d_handles) cudaFree(d_handles);
+        if (d_mine) cudaFree(d_mine);
+        if (ctx->d_mailbox) { cudaFree(ctx->d_mailbox); ctx->d_mailbox = nullptr; }
+        cudaGetLastError();
+        return;
+    }
+    cudaMemcpyAsync(d_mine, blob, sizeof(blob), cudaMemcpyHostToDevice, ctx->stream);
+    int r = g_nccl.AllGather(d_mine, d_handles, sizeof(blob), kNcclInt8, ctx->comm, ctx->stream);
+    if (r == 0) {
+        cudaMemcpyAsync(all.data(), d_handles, sizeof(mine) * ctx->nranks, cudaMemcpyDeviceToHost, ctx->stream);
+        if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) r = 1;
+    }
+    if (r != 0) ok = false;
+    peer::View v{};
+    v.nranks = ctx->nranks; v.rank = ctx->rank;
+    for (int q = 0; q < ctx->nranks && ok; ++q) {
+        static const unsigned char zero[sizeof(cudaIpcMemHandle_t)] = {0};
+        if (memcmp(&all[q], zero, sizeof(zero)) == 0) { ok = false; break; }      // that rank could not export
+        if (q == ctx->rank) { v.box[q] = ctx->d_mailbox; continue; }
+        void* ptr = nullptr;
+        if (cudaIpcOpenMemHandle(&ptr, all[q], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = false; break; }
+        ctx->peer_ptr[q] = ptr;
+        v.box[q] = (peer::Mailbox*)ptr;
+    }
+    // agree: peer mode only if EVERY rank mapped everything (one more tiny collective: min over ranks)
+    double* d_flag = ctx->d_small + 700;
+    const double flag = ok ? 1.0 : 0.0;
+    cudaMemcpyAsync(d_flag, &flag, sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+    // sum of the flags == nranks  <=>  all ok
+    double total = 0.0;
+    if (g_nccl.AllReduce(d_flag, d_flag, 1, kNcclFloat64, kNcclSum, ctx->comm, ctx->stream) == 0) {
+        cudaMemcpyAsync(&total, d_flag, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+        cudaStreamSynchronize(ctx->stream);
+    }
+    cudaFree(d_handles); cudaFree(d_mine);
+    if (total > (double)ctx->nranks - 0.5) {
+        ctx->peer_view = v;
+        ctx->peer_ok = true;
+    } else {
+        for (int q = 0; q < peer::kMaxRanks; ++q)
+            if (ctx->peer_ptr[q]) { cudaIpcCloseMemHandle(ctx->peer_ptr[q]); ctx->peer_ptr[q] = nullptr; }
+        if (ctx->d_mailbox) { cudaFree(ctx->d_mailbox); ctx->d_mailbox = nullptr; }
+        cudaGetLastError();
+    }
+}
+
 int dcreg_comm_init(dcreg_ctx* ctx, const uint8_t nccl_unique_id[128], int rank, int nranks) {
     if (!ctx || !nccl_unique_id || nranks < 1 || rank < 0 || rank >= nranks) return DCREG_BAD_ARG;
     if (!g_nccl.load(ctx->err)) return DCREG_NCCL_ERROR;
@@ -1563,16 +1908,26 @@ int dcreg_comm_init(dcreg_ctx* ctx, const uint8_t nccl_unique_id[128], int rank,
         return DCREG_NCCL_ERROR;
     }
     ctx->rank = rank; ctx->nranks = nranks;
+    setup_peer_mailboxes(ctx);
+    if (ctx->graph_exec) { cudaGraphExecDestroy(ctx->graph_exec); ctx->graph_exec = nullptr; ctx->graph_key.clear(); }
     return DCREG_OK;
+}
+
+int dcreg_comm_mode(const dcreg_ctx* ctx) {
+    if (!ctx || !ctx->comm) return 0;
+    return ctx->peer_ok ? 2 : 1;
 }
 
 int dcreg_comm_destroy(dcreg_ctx* ctx) {
     if (!ctx) return DCREG_BAD_ARG;
-    if (ctx->comm && g_nccl.CommDestroy) {
-        cudaStreamSynchronize(ctx->stream);
-        g_nccl.CommDestroy(ctx->comm);
-    }
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (int q = 0; q < peer::kMaxRanks; ++q)
+        if (ctx->peer_ptr[q]) { cudaIpcCloseMemHandle(ctx->peer_ptr[q]); ctx->peer_ptr[q] = nullptr; }
+    if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);     // (a collective: peers are still alive here)
+    if (ctx->d_mailbox) { cudaFree(ctx->d_mailbox); ctx->d_mailbox = nullptr; }
+    ctx->peer_ok = false; ctx->peer_view = peer::View{};
     ctx->comm = nullptr; ctx->rank = 0; ctx->nranks = 1;
+    if (ctx->graph_exec) { cudaGraphExecDestroy(ctx->graph_exec); ctx->graph_exec = nullptr; ctx->graph_key.clear(); }
     return DCREG_OK;
 }
 

@@ -71,9 +71,11 @@ __device__ __forceinline__ double f32_to_f64(float f) {
 
 // Per-slot front: residual, weight, gate, float32 round trips, Jacobian row in the world frame.
 // Output c[8] = [k (Rp x u'), k u', b, r], all zeros for an invalid slot (no plane or gated out).
+// slope / gate: dcreg_icp_params::weight_slope / weight_gate (0.9 / 0.1 in the reference, icp_test_runner.cpp:1776, 1785)
 template <bool kUseWd>
 __device__ __forceinline__ void slot_front(const Pose& P, double px, double py, double pz, double nx, double ny,
-                                           double nz, double d, bool has, double (&c)[8], int& neff) {
+                                           double nz, double d, bool has, double (&c)[8], int& neff,
+                                           double slope = 0.9, double gate = 0.1) {
     const double wx = fma(P.R[2], pz, fma(P.R[1], py, P.R[0] * px));     // Rp (no translation)
     const double wy = fma(P.R[5], pz, fma(P.R[4], py, P.R[3] * px));
     const double wz = fma(P.R[8], pz, fma(P.R[7], py, P.R[6] * px));
@@ -81,8 +83,8 @@ __device__ __forceinline__ void slot_front(const Pose& P, double px, double py, 
     const double qy = round_f32(wy + P.t[1]);
     const double qz = round_f32(wz + P.t[2]);
     const double rr = fma(nx, qx, fma(ny, qy, fma(nz, qz, d)));   // icp_test_runner.cpp:1774
-    const double ss = 1.0 - 0.9 * fabs(rr);                       // :1776 (max(0, .) is implied by the gate)
-    const bool valid = has && (ss > 0.1);                         // :1785
+    const double ss = 1.0 - slope * fabs(rr);                     // :1776 (max(0, .) is implied by the gate >= 0)
+    const bool valid = has && (ss > gate);                        // :1785
     const double s = valid ? ss : 0.0;
     const double r = valid ? rr : 0.0;
     double ux = round_f32(s * nx);                                // coeff.x/y/z (:1787-1789)

@@ -31,6 +31,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "k1_reduce.cuh"
+#include "peer_reduce.cuh"
 
 namespace k1s {
 
@@ -49,6 +50,9 @@ struct Args {
     double* partials;            // [grid][k1::kGramPart]
     unsigned int* counter;
     double* acc;                 // [k2::kAcc] final, body frame
+    double npt_override;         // >= 0: N_corr_pt of this rank as counted by the caller's correspondence stage (host-kd-tree
+                                 // mode: the reference counts BEFORE the plane gates, icp_test_runner.cpp:1726-1731, 1856)
+    peer::View peer;             // multi-GPU: sum over ranks inside the last block (nranks <= 1: none)
     int debug;                   // profiling only (tools/sweep_k1.py): 4 = exit at once, 3 = after the stream loop, 2 = before the grid reduction
 };
 
@@ -154,6 +158,7 @@ constexpr int kPk = 32, kPkG = 21, kPkR2 = 27, kPkB2 = 28, kPkNeff = 29, kPkNpt 
 struct TailSmem {
     double red[kWarpsPerBlock][kPk];
     double fin[kPk];
+    double acc[kPk];             // body-frame accumulators (k2::kAcc layout): input of the in-kernel solve step
     bool is_last;
 };
 
@@ -162,12 +167,16 @@ __device__ __forceinline__ int pk_index(int a, int b) {           // packed uppe
     return i * 6 - (i * (i - 1)) / 2 + (j - i);
 }
 
-// Grid reduction of the packed partials.  Every lane of every warp calls this with its warp's total number `lane`.
-// warp totals -> block partial (32 doubles, one coalesced 256 B row) -> atomic ticket -> the last block sums the
-// rows in a fixed order (warp w: rows w, w + 8, ...; all of a lane's loads are in flight at once), applies the
-// world -> body congruence with blkdiag(R, R) and writes acc_out[k2::kAcc].  Deterministic for a given grid size.
-__device__ __forceinline__ void finish_packed(double mine, TailSmem& ts, double* partials, unsigned int* counter,
-                                              const double* R, double* acc_out) {
+// Grid reduction of the packed partials, in two steps so that the multi-GPU exchange (peer_reduce.cuh) and the solve
+// step (the loop kernel) can sit between / behind them inside the same kernel.
+//
+// reduce_to_fin: every lane of every warp calls this with its warp's total number `lane`.  warp totals -> block
+// partial (32 doubles, one coalesced 256 B row) -> atomic ticket -> the last block sums the rows in a fixed order
+// (warp w: rows w, w + 8, ...; all of a lane's loads are in flight at once) into ts.fin (world frame, packed kPk
+// layout).  Returns true in every thread of the last block.  Deterministic for a given grid size.
+// `nblocks` = blocks that feed this ticket (gridDim.x; the loop kernel has one ticket per trial = per blockIdx.y).
+__device__ __forceinline__ bool reduce_to_fin(double mine, TailSmem& ts, double* partials, unsigned int* counter,
+                                              int block, int nblocks) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     ts.red[warp][lane] = mine;
     __syncthreads();
@@ -175,28 +184,28 @@ __device__ __forceinline__ void finish_packed(double mine, TailSmem& ts, double*
         double s = 0.0;
 #pragma unroll
         for (int w = 0; w < kWarpsPerBlock; ++w) s += ts.red[w][lane];
-        partials[(size_t)blockIdx.x * kPk + lane] = s;
+        partials[(size_t)block * kPk + lane] = s;
         __threadfence();
         __syncwarp();
-        if (lane == 0) ts.is_last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+        if (lane == 0) ts.is_last = (atomicAdd(counter, 1u) == (unsigned)nblocks - 1u);
     }
     __syncthreads();
-    if (!ts.is_last) return;
+    if (!ts.is_last) return false;
     __threadfence();
     {
         constexpr int kRows = 40;                                  // rows in flight per lane and trip
-        const int nb = (int)gridDim.x;
         double s = 0.0;
-        for (int b0 = warp; b0 < nb; b0 += kWarpsPerBlock * kRows) {
+        for (int b0 = warp; b0 < nblocks; b0 += kWarpsPerBlock * kRows) {
             double t[kRows];
 #pragma unroll
             for (int u = 0; u < kRows; ++u) {
                 const int b = b0 + u * kWarpsPerBlock;
-                t[u] = (b < nb) ? __ldcg(partials + (size_t)b * kPk + lane) : 0.0;
+                t[u] = (b < nblocks) ? __ldcg(partials + (size_t)b * kPk + lane) : 0.0;
             }
 #pragma unroll
             for (int u = 0; u < kRows; ++u) s += t[u];
         }
+        __syncthreads();                                          // red[][] is free again
         ts.red[warp][lane] = s;
     }
     __syncthreads();
@@ -205,10 +214,16 @@ __device__ __forceinline__ void finish_packed(double mine, TailSmem& ts, double*
 #pragma unroll
         for (int w = 0; w < kWarpsPerBlock; ++w) s += ts.red[w][lane];
         ts.fin[lane] = s;
+        if (lane == 0) *counter = 0u;                             // every block has arrived: ready for the next launch
     }
     __syncthreads();
-    // world -> body: H_body = Q^T H Q, g_body = Q^T g with Q = blkdiag(R, R); one thread per output entry
-    const double* fin = ts.fin;
+    return true;
+}
+
+// world -> body: H_body = Q^T H Q, g_body = Q^T g with Q = blkdiag(R, R); one thread per output entry.  fin: packed
+// world-frame totals (shared memory), out: k2::kAcc doubles (shared or global).  Called by all threads of the block.
+__device__ __forceinline__ void congruence(const double* fin, const double* R, double* out) {
+    const int tid = threadIdx.x;
     if (tid < 36) {
         const int i = tid / 6, j = tid % 6;
         if (j >= i) {
@@ -218,21 +233,20 @@ __device__ __forceinline__ void finish_packed(double mine, TailSmem& ts, double*
             for (int k = 0; k < 3; ++k)
 #pragma unroll
                 for (int l = 0; l < 3; ++l) acc = fma(R[k * 3 + ii] * fin[pk_index(bi + k, bj + l)], R[l * 3 + jj], acc);
-            acc_out[pk_index(i, j)] = acc;
+            out[pk_index(i, j)] = acc;
         }
     } else if (tid < 42) {
         const int i = tid - 36, bi = (i / 3) * 3, ii = i % 3;
         double acc = 0.0;
 #pragma unroll
         for (int k = 0; k < 3; ++k) acc = fma(R[k * 3 + ii], fin[kPkG + bi + k], acc);
-        acc_out[21 + i] = acc;
+        out[21 + i] = acc;
     } else if (tid == 42) {
-        acc_out[k2::kAccSumR2] = fin[kPkR2];
-        acc_out[k2::kAccNeff] = fin[kPkNeff];
-        acc_out[k2::kAccNpt] = fin[kPkNpt];
-        acc_out[k2::kAccSumB2] = fin[kPkB2];
-        acc_out[k2::kAcc - 1] = 0.0;
-        *counter = 0u;
+        out[k2::kAccSumR2] = fin[kPkR2];
+        out[k2::kAccNeff] = fin[kPkNeff];
+        out[k2::kAccNpt] = fin[kPkNpt];
+        out[k2::kAccSumB2] = fin[kPkB2];
+        out[k2::kAcc - 1] = 0.0;
     }
 }
 
@@ -385,7 +399,11 @@ __global__ void __launch_bounds__(kThreads, 2) reduce_stream_kernel(const __grid
         }
     }
     if (a.debug == 2) { if (v[0] == 1.2345) a.acc[0] = v[0]; return; }
-    finish_packed(v[0], sm.tail, a.partials, a.counter, a.pose.R, a.acc);
+    if (!reduce_to_fin(v[0], sm.tail, a.partials, a.counter, (int)blockIdx.x, (int)gridDim.x)) return;
+    if (a.npt_override >= 0.0 && tid == 0) sm.tail.fin[kPkNpt] = a.npt_override;
+    __syncthreads();
+    peer::all_reduce32(a.peer, sm.tail.fin, sm.tail.red);
+    congruence(sm.tail.fin, a.pose.R, a.acc);
 }
 
 }  // namespace k1s

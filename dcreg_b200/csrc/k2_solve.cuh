@@ -36,7 +36,23 @@ struct IcpState {               // device-resident loop state, written only by K
     int seeds;                  // 1: the iteration kernel that just ran left neighbour records behind
     int coherent_used;          // mode the iteration kernel that just ran was in (it reads it from `coherent`)
     int coherent;               // 1: the next iteration may use the records (the last update was small)
+    int pad0;
+    unsigned long long t_last;  // globaltimer (ns) at the end of the previous solve step / at run start (iter_time_ms)
 };
+
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+// IterationLogData::iter_time_ms (icp_test_runner.cpp:1695 tic, :1973 toc): device time since the previous step ended
+__device__ __forceinline__ double stamp_iteration(IcpState* st) {
+    const unsigned long long now = globaltimer_ns();
+    const double ms = (double)(now - st->t_last) * 1e-6;
+    st->t_last = now;
+    return ms;
+}
 
 // after the pose update: decide the next iteration's mode (see icp_iter2_kernel)
 __device__ __forceinline__ void note_step(IcpState* st, const double* dx, double lever, double max_step) {
@@ -153,7 +169,8 @@ __device__ inline void analyze_and_solve(const double* v27, const dcreg_icp_para
         a->aligned_V_rot[i] = a->aligned_V_trans[i] = a->schur_V_rot[i] = a->schur_V_trans[i] = e;
     }
     for (int i = 0; i < 3; ++i) { a->rot_indices[i] = a->trans_indices[i] = i; }
-    a->reserved1[0] = a->reserved1[1] = 0;
+    a->schur_singular = 0; a->reserved1 = 0;
+    for (int i = 0; i < 36; ++i) a->W_adaptive[i] = 0.0;                  // dcreg.hpp:52: reset, never written by a released handler
 
     // ---- full EVD / "SVD" of H (dcreg.hpp:62-89) ----
     double W[36], lam[6], V[36];
@@ -236,6 +253,7 @@ __device__ inline void analyze_and_solve(const double* v27, const dcreg_icp_para
     } else {
         for (int i = 0; i < 3; ++i) a->lambda_schur_rot[i] = a->lambda_schur_trans[i] = NaN;
         a->cond_schur_rot = a->cond_schur_trans = (double)INFINITY;
+        a->schur_singular = 1;                               // icp_test_runner.cpp:2464 (a warning there)
     }
 
     // ---- detection (dcreg.hpp:94-162 + paper Eq. 20-21 for the Schur case) ----
@@ -385,8 +403,10 @@ __device__ inline void icp_step(const double* acc, IcpState* st, const dcreg_icp
     }
     if (n_eff < prm.min_effective_points) {                 // icp_test_runner.cpp:1847-1854
         st->iter = iter + 1; st->done = 1; st->converged = 0; st->status = DCREG_NOT_ENOUGH_POINTS;
+        const double ms = stamp_iteration(st);
         if (rec) {
             rec->status = DCREG_NOT_ENOUGH_POINTS; rec->rmse = 0.0; rec->fitness = 0.0; rec->objective = 0.0;
+            rec->iter_time_ms = ms;
             for (int i = 0; i < 6; ++i) { rec->gradient[i] = 0.0; rec->dx[i] = 0.0; }
             for (int r = 0; r < 3; ++r) {
                 for (int c = 0; c < 3; ++c) rec->T[r * 4 + c] = st->R[r * 3 + c];
@@ -408,7 +428,16 @@ __device__ inline void icp_step(const double* acc, IcpState* st, const dcreg_icp
     }
     if (!finite) {                                          // icp_test_runner.cpp:1942-1950
         st->done = 1; st->converged = 0; st->status = DCREG_NONFINITE_UPDATE;
-        if (rec) { rec->status = DCREG_NONFINITE_UPDATE; for (int i = 0; i < 6; ++i) rec->dx[i] = 0.0; }
+        const double ms = stamp_iteration(st);
+        if (rec) {
+            rec->status = DCREG_NONFINITE_UPDATE; rec->objective = 0.5 * acc[kAccSumB2]; rec->iter_time_ms = ms;
+            for (int i = 0; i < 6; ++i) rec->dx[i] = 0.0;
+            for (int r = 0; r < 3; ++r) {
+                for (int c = 0; c < 3; ++c) rec->T[r * 4 + c] = st->R[r * 3 + c];
+                rec->T[r * 4 + 3] = st->t[r];
+            }
+            rec->T[12] = rec->T[13] = rec->T[14] = 0.0; rec->T[15] = 1.0;
+        }
         return;
     }
     boxplus(st->R, st->t, dx);                              // icp_test_runner.cpp:1953
@@ -434,6 +463,8 @@ __device__ inline void icp_step(const double* acc, IcpState* st, const dcreg_icp
     } else if (st->iter >= prm.max_iterations) {
         st->done = 1;
     }
+    const double ms = stamp_iteration(st);                  // icp_test_runner.cpp:1973
+    if (rec) rec->iter_time_ms = ms;
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -520,8 +551,10 @@ __device__ inline void icp_step_warp_ours(const double* acc, IcpState* st, const
     if (n_eff < prm.min_effective_points) {                 // icp_test_runner.cpp:1847-1854 (uniform branch)
         if (lane == 0) {
             st->iter = iter + 1; st->done = 1; st->converged = 0; st->status = DCREG_NOT_ENOUGH_POINTS;
+            const double ms = stamp_iteration(st);
             if (rec) {
                 rec->status = DCREG_NOT_ENOUGH_POINTS; rec->rmse = 0.0; rec->fitness = 0.0; rec->objective = 0.0;
+                rec->iter_time_ms = ms;
                 for (int i = 0; i < 6; ++i) { rec->gradient[i] = 0.0; rec->dx[i] = 0.0; }
                 for (int r = 0; r < 3; ++r) {
                     for (int c = 0; c < 3; ++c) rec->T[r * 4 + c] = st->R[r * 3 + c];
@@ -618,8 +651,18 @@ __device__ inline void icp_step_warp_ours(const double* acc, IcpState* st, const
         if (lane < 6) rec->gradient[lane] = -acc[21 + lane];
     }
     if (!finite) {                                          // icp_test_runner.cpp:1942-1950
-        if (lane == 0) { st->done = 1; st->converged = 0; st->status = DCREG_NONFINITE_UPDATE; }
-        if (rec) { if (lane == 0) rec->status = DCREG_NONFINITE_UPDATE; if (lane < 6) rec->dx[lane] = 0.0; }
+        if (lane == 0) {
+            st->done = 1; st->converged = 0; st->status = DCREG_NONFINITE_UPDATE;
+            const double ms = stamp_iteration(st);
+            if (rec) { rec->status = DCREG_NONFINITE_UPDATE; rec->iter_time_ms = ms; }
+        }
+        if (rec) {
+            if (lane < 6) rec->dx[lane] = 0.0;
+            if (lane < 16) {
+                const int r = lane / 4, c = lane % 4;
+                rec->T[lane] = r == 3 ? (c == 3 ? 1.0 : 0.0) : (c == 3 ? sm.Rt[9 + r] : sm.Rt[r * 3 + c]);
+            }
+        }
         return;
     }
     for (int e = lane; e < 36; e += 32) st->H_last[e] = sm.H[e];     // matAtA_last, icp_test_runner.cpp:1965
@@ -634,6 +677,8 @@ __device__ inline void icp_step_warp_ours(const double* acc, IcpState* st, const
         } else if (st->iter >= prm.max_iterations) {
             st->done = 1;
         }
+        const double ms = stamp_iteration(st);               // icp_test_runner.cpp:1973
+        if (rec) rec->iter_time_ms = ms;
     }
     __syncwarp();
     if (lane < 9) st->R[lane] = sm.Rt[lane];

@@ -12,8 +12,8 @@
 // by method NAME (only Ours, NONE, ME-SR, FCN-SR, ME-TSVD, ME-TReg reach the SO(3) path; others print the reference's
 // "Can not recognize the method" line, since the XICP / SuperLoc / Open3D baselines are out of scope); the per-iteration
 // CSV swaps its two error columns (icp_test_runner.cpp:1457-1458); unknown enum strings map to the first enumerator.
-// Differences: `Time_ms` per iteration is the run time divided by the iteration count (the loop never returns to the host
-// between iterations); `<method>_error.pcd` (jet-coloured visual artefact) is not written.
+// `Time_ms` per iteration is dcreg_iter_log::iter_time_ms, the device's own tic/toc of that iteration (the loop never
+// returns to the host between iterations).  Difference: `<method>_error.pcd` (jet-coloured visual artefact) is not written.
 #include <algorithm>
 #include <chrono>
 #include <cmath>
@@ -303,7 +303,7 @@ private:
         for (int i = 0; i < nrec; ++i) {
             IterData d;
             d.g = log[i];
-            d.iter_time_ms = n_iter > 0 ? r.time_ms / n_iter : 0.0;
+            d.iter_time_ms = log[i].iter_time_ms;   // device-measured tic/toc of this iteration (icp_test_runner.cpp:1695, 1973)
             Mat4 Ti; std::memcpy(Ti.m, log[i].T, sizeof(Ti.m));
             const PoseError e = calculatePoseError(config_.gt_matrix, Ti);
             d.rot_error_vs_gt = e.rotation_error; d.trans_error_vs_gt = e.translation_error;

@@ -3,6 +3,8 @@
 C2  make_cylinder : the shipped cylinder's geometry (wall R = 40 m, z in [0, 20] + floor disc z = 0) at any size
 C3  make_parking  : ground-dominated local map + sparse verticals, LiDAR-like frame (stand-in, pair not shipped)
 C4  make_corridor : two parallel walls + floor + ceiling, rank-deficient along x
+C5  trial_poses   : seeded perturbations t ~ U[-1, 1]^3 m, rpy ~ U[-3, 3]^3 deg for the Monte-Carlo
+    load_pcd_xyz  : PCD v0.7 `DATA binary` with float32 fields (the shipped clouds)
 """
 from __future__ import annotations
 
@@ -81,3 +83,30 @@ def make_parking(n_map=500_000, n_scan=6_000, seed=43, extent=60.0, max_range=30
     pick = rng.choice(cand, size=min(n_scan, cand.size), replace=False)
     scan = (tgt[pick].astype(np.float64) + rng.normal(0, 0.005, (pick.size, 3))).astype(np.float32)
     return np.ascontiguousarray(scan), np.ascontiguousarray(tgt)
+
+
+def trial_poses(n, seed=45, max_trans=1.0, max_rot_deg=3.0):
+    """(n, 4, 4) initial poses of a perturbation Monte-Carlo (BASELINE.json configs[4])."""
+    rng = np.random.default_rng(seed)
+    t = rng.uniform(-max_trans, max_trans, (n, 3))
+    rpy = np.deg2rad(rng.uniform(-max_rot_deg, max_rot_deg, (n, 3)))
+    return np.array([pose6d_to_matrix(t[i, 0], t[i, 1], t[i, 2], rpy[i, 0], rpy[i, 1], rpy[i, 2]) for i in range(n)])
+
+
+def load_pcd_xyz(path):
+    """x, y, z columns of a PCD v0.7 file with `DATA binary` and 4-byte float fields (pcl::PointXYZI on disk)."""
+    with open(path, "rb") as f:
+        raw = f.read()
+    head_end = raw.index(b"DATA binary") + len(b"DATA binary")
+    head_end = raw.index(b"\n", head_end - 1) + 1
+    hdr = {}
+    for ln in raw[:head_end].decode("ascii", "replace").splitlines():
+        tok = ln.split()
+        if tok and not tok[0].startswith("#"):
+            hdr[tok[0]] = tok[1:]
+    if any(s != "4" for s in hdr["SIZE"]) or any(t != "F" for t in hdr["TYPE"]):
+        raise ValueError("only 4-byte float fields are supported")
+    nf, npts = len(hdr["FIELDS"]), int(hdr["POINTS"][0])
+    a = np.frombuffer(raw, dtype="<f4", count=npts * nf, offset=head_end).reshape(npts, nf)
+    cols = [hdr["FIELDS"].index(c) for c in ("x", "y", "z")]
+    return np.ascontiguousarray(a[:, cols], dtype=np.float32)

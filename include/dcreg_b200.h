@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define DCREG_ABI_VERSION 1
+#define DCREG_ABI_VERSION 2
 
 /* -------------------------------------------------------------------------------------------
  * Status codes.  Reference convention: bool return + std::cerr text
@@ -30,7 +30,9 @@ typedef enum dcreg_status {
     DCREG_OK = 0,
     DCREG_NOT_ENOUGH_POINTS = 1,   /* < 10 effective correspondences (icp_test_runner.cpp:1847) */
     DCREG_NONFINITE_UPDATE = 2,    /* solver returned non-finite dx (icp_test_runner.cpp:1942)  */
-    DCREG_SINGULAR_BLOCK = 3,      /* H_RR or H_tt not invertible (icp_test_runner.cpp:2464)    */
+    DCREG_SINGULAR_BLOCK = 3,      /* never RETURNED: the reference only warns when H_RR or H_tt is not invertible
+                                      (icp_test_runner.cpp:2464) and carries on with cond = inf; the warning is
+                                      surfaced per iteration as dcreg_analysis.schur_singular.  Value kept reserved. */
     DCREG_CUDA_ERROR = 4,
     DCREG_NCCL_ERROR = 5,
     DCREG_BAD_ARG = 6,
@@ -78,8 +80,8 @@ typedef struct dcreg_icp_params {
     double std_reg_gamma;          /* STD_REG_GAMMA                           (0.01)  */
     /* compile-time constants of the reference, exposed with the reference values */
     double plane_thickness;        /* 0.2   icp_test_runner.cpp:1772 */
-    double weight_slope;           /* 0.9   icp_test_runner.cpp:1776 */
-    double weight_gate;            /* 0.1   icp_test_runner.cpp:1785 */
+    double weight_slope;           /* 0.9   icp_test_runner.cpp:1776: s = 1 - weight_slope |r|              */
+    double weight_gate;            /* 0.1   icp_test_runner.cpp:1785: slot kept when s > weight_gate         */
     double min_normal_norm;        /* 1e-6  icp_test_runner.cpp:1750 */
     int32_t min_effective_points;  /* 10    icp_test_runner.cpp:1847 */
     int32_t fixed_iterations;      /* 1: ignore the convergence test and always run max_iterations
@@ -102,8 +104,10 @@ typedef struct dcreg_analysis {
     double schur_V_rot[9], schur_V_trans[9];             /* eigenvectors in columns */
     double aligned_V_rot[9], aligned_V_trans[9];         /* paper Alg. 2 (log only) */
     int32_t rot_indices[3], trans_indices[3];
-    int32_t reserved1[2];
+    int32_t schur_singular;        /* 1: H_tt or H_RR not invertible, Schur complements skipped (icp_test_runner.cpp:2464) */
+    int32_t reserved1;
     double P_preconditioner[36];   /* paper Eq. 43-46; identity unless SCHUR detection */
+    double W_adaptive[36];         /* utils.hpp:446; zero: no released handler writes it (dcreg.hpp:52) */
     double pcg_residual;           /* ||g - H dx||_2 at exit of the PCG solve */
 } dcreg_analysis;
 
@@ -115,6 +119,10 @@ typedef struct dcreg_iter_log {
     int32_t n_effective;           /* corr_num / effective_points */
     int32_t n_corr_pt;             /* correspondence_pt_count (5th NN within radius) */
     double rmse, fitness, objective;
+    double iter_time_ms;           /* IterationLogData::iter_time_ms (utils.hpp:174-249; tic at the top of the iteration,
+                                      toc after the update, icp_test_runner.cpp:1695, 1973): device time between the
+                                      end of the previous solve step (run start for iteration 0) and the end of this
+                                      one, from the GPU's globaltimer */
     double gradient[6];            /* -A^T b */
     double H27[27];                /* 21 upper-tri of A^T A (row-major upper) + 6 rhs A^T b */
     double dx[6];
@@ -193,6 +201,18 @@ int dcreg_solve_pcg(dcreg_ctx* ctx, const double A[36], const double b[6], const
 int dcreg_icp_run(dcreg_ctx* ctx, const dcreg_icp_params* params, const double T_init[16],
                   double T_out[16], dcreg_iter_log* log, int log_cap, int* n_iterations,
                   int* converged);
+/* Many registrations of the SAME source against the SAME target from different initial poses, side by side in one
+ * sequence of launches (trial = grid y-dimension; each trial owns its loop state, neighbour records and log slice, and
+ * stops on its own convergence test).  Replaces the `num_runs` loop of TestRunner::runSingleTest
+ * (icp_test_runner.cpp:331-345: `for run in 0..num_runs: runSingleTest`) and is what a perturbation Monte-Carlo
+ * (BASELINE.json configs[4]) calls.  T_init / T_out: n_trials row-major 4x4 matrices; n_iterations / converged / status:
+ * n_trials ints (status[t] = what dcreg_icp_run would have returned for trial t; any may be NULL except T_init, T_out);
+ * log: n_trials x log_cap records (trial-major) or NULL.  Every trial's result is bit-identical to a dcreg_icp_run
+ * with the same T_init (same kernels, same summation order).  Not available on a sharded context: trials are
+ * independent, distribute them over ranks instead.  Needs the dense target grid. */
+int dcreg_icp_run_batch(dcreg_ctx* ctx, const dcreg_icp_params* params, int n_trials, const double* T_init,
+                        double* T_out, int* n_iterations, int* converged, int* status, dcreg_iter_log* log,
+                        int log_cap);
 /* Same loop, but correspondences are supplied by the caller each iteration through a callback
  * (host kd-tree mode, "PR1"): planes are 4*n doubles (nx,ny,nz,d), all-zero = none. */
 typedef int (*dcreg_plane_callback)(void* user, const double T[16], double* planes4,
@@ -212,13 +232,18 @@ int dcreg_last_covariance(dcreg_ctx* ctx, double cov[36]);
 int dcreg_point_to_point_metrics(dcreg_ctx* ctx, const double T[16], double error_threshold, double out[4]);
 
 /* ---- multi-GPU: point-block sharding ---------------------------------------
- * Each rank holds a contiguous block of source slots; after K1 the 27+3 accumulators are summed
- * over ranks (one ncclAllReduce of 30 doubles on the context's stream), then every rank runs K2
- * redundantly.  nccl_unique_id is the 128-byte ncclUniqueId created by dcreg_comm_unique_id on
+ * Each rank holds a contiguous block of source slots; the 27+5 accumulators are summed over ranks
+ * once per iteration (inside the reducing kernel over peer memory, see dcreg_comm_mode; one
+ * ncclAllReduce of 32 doubles on the context's stream as the fallback), then every rank runs K2
+ * redundantly on bit-identical sums.  nccl_unique_id is the 128-byte ncclUniqueId created by dcreg_comm_unique_id on
  * rank 0 and distributed by the caller (e.g. torch.distributed broadcast). */
 int dcreg_comm_unique_id(dcreg_ctx* ctx, uint8_t id_out[128]);
 int dcreg_comm_init(dcreg_ctx* ctx, const uint8_t nccl_unique_id[128], int rank, int nranks);
 int dcreg_comm_destroy(dcreg_ctx* ctx);
+/* How the per-iteration sum over ranks is carried: 0 = no communicator, 1 = ncclAllReduce behind the reducing kernel
+ * (fallback), 2 = peer-memory mailboxes over NVLink inside the reducing kernel's last block (one kernel per iteration,
+ * bit-identical sums on every rank).  dcreg_comm_init picks 2 when every rank could map every peer (cudaIpc). */
+int dcreg_comm_mode(const dcreg_ctx* ctx);
 /* Total number of source points over all ranks (denominator of `fitness`); defaults to local n. */
 int dcreg_set_global_source_count(dcreg_ctx* ctx, int64_t n_total);
 

@@ -40,7 +40,8 @@ typedef struct {
     int pcg_max_iter, fixed_iterations;
     double std_reg_gamma;
     int thread_mode;   /* 0 reference-faithful (8 threads, serial H), 1 best-effort (all cores) */
-    int reserved;
+    int n_threads;     /* > 0: explicit OpenMP team size (bench.py picks it from the CPUs this process may really use);
+                          0: mode 0 -> 8 (icp_test_runner.cpp:1714), mode 1 -> omp_get_max_threads() */
 } orc_params;
 
 typedef struct {
@@ -523,7 +524,7 @@ int orc_icp_run(const orc_scene* sc, const orc_params* prm, const double* T_init
     unsigned char* flag = (unsigned char*)malloc((size_t)n);
     int status = 0, iters = 0; *converged = 0;
 #ifdef _OPENMP
-    const int nthreads = prm->thread_mode == 0 ? 8 : omp_get_max_threads();
+    const int nthreads = prm->n_threads > 0 ? prm->n_threads : (prm->thread_mode == 0 ? 8 : omp_get_max_threads());
 #else
     const int nthreads = 1;
 #endif

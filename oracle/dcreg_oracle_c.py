@@ -20,7 +20,7 @@ class Params(C.Structure):
                 ("conv_trans", C.c_double), ("cond_thresh", C.c_double), ("eig_thresh", C.c_double),
                 ("kappa_target", C.c_double), ("pcg_tol", C.c_double), ("pcg_max_iter", C.c_int),
                 ("fixed_iterations", C.c_int), ("std_reg_gamma", C.c_double), ("thread_mode", C.c_int),
-                ("reserved", C.c_int)]
+                ("n_threads", C.c_int)]
 
 
 class Iter(C.Structure):
@@ -70,10 +70,10 @@ def load():
 
 def make_params(search_radius=1.0, max_iterations=30, detection=1, handling=3, use_weight_derivative=False,
                 conv_rot=1e-5, conv_trans=1e-3, cond_thresh=10.0, eig_thresh=120.0, kappa_target=1.0, pcg_tol=1e-6,
-                pcg_max_iter=10, fixed_iterations=False, std_reg_gamma=0.01, thread_mode=1) -> Params:
+                pcg_max_iter=10, fixed_iterations=False, std_reg_gamma=0.01, thread_mode=1, n_threads=0) -> Params:
     return Params(search_radius, max_iterations, detection, handling, int(use_weight_derivative), conv_rot, conv_trans,
                   cond_thresh, eig_thresh, kappa_target, pcg_tol, pcg_max_iter, int(fixed_iterations), std_reg_gamma,
-                  thread_mode, 0)
+                  thread_mode, int(n_threads))
 
 
 class Scene:

@@ -34,14 +34,14 @@ def test_every_symbol_exported(lib):
 
 def test_abi_version_and_struct_sizes(lib):
     from dcreg_b200 import api
-    assert lib.dcreg_abi_version() == 1
+    assert lib.dcreg_abi_version() == 2
     p = api.default_params()
     assert p.search_radius == 1.0 and p.max_iterations == 30 and p.pcg_max_iter == 10
     assert p.cond_thresh == 10.0 and p.eig_thresh == 120.0 and p.kappa_target == 1.0 and p.std_reg_gamma == 0.01
     assert p.plane_thickness == 0.2 and p.weight_slope == 0.9 and p.weight_gate == 0.1 and p.min_effective_points == 10
     # sizes of the C structs as compiled by g++/nvcc (checked in test_struct_sizes_match_c below)
     assert ctypes.sizeof(api.IcpParams) == 128
-    assert ctypes.sizeof(api.Analysis) == 896 and ctypes.sizeof(api.IterLog) == 1376
+    assert ctypes.sizeof(api.Analysis) == 1184 and ctypes.sizeof(api.IterLog) == 1672
 
 
 def test_struct_sizes_match_c(tmp_path):

@@ -1,4 +1,9 @@
-"""2+ rank check (torchrun): sharded ICP (point blocks + ncclAllReduce of 32 doubles) == single-GPU ICP."""
+"""2+ rank check (torchrun): the point-sharded registration == the single-GPU registration, in both exchange modes.
+
+mode 2: the sum over ranks inside the iteration kernel's last block over peer memory (peer_reduce.cuh), solve step folded
+mode 1: ncclAllReduce of 32 doubles behind the iteration kernel + separate solve kernel (fallback, DCREG_NO_PEER=1)
+Also checks the sharded K1 seam (dcreg_reduce_normal_equations on a shard == the unsharded sums, identical on all ranks).
+"""
 import os, sys
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -11,27 +16,56 @@ from dcreg_b200.scenes import make_cylinder, g2_initial_pose
 
 rank, local, world = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"]), int(os.environ["WORLD_SIZE"])
 torch.cuda.set_device(local)
-dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-pts = make_cylinder(60_000, seed=42)
+dev = torch.device("cuda", local)
+dist.init_process_group("nccl", device_id=dev)
+n_pts = int(os.environ.get("SHARDED_CHECK_POINTS", 60_000))
+pts = make_cylinder(n_pts, seed=42)
 T0 = g2_initial_pose()
-prm = default_params(max_iterations=30, fixed_iterations=1, kappa_target=10.0)   # long enough to reach the record-reusing mode
-ctx = Context(local)
-ctx.set_target(pts, 1.0)
-# single-GPU reference on every rank
-ctx.set_source(pts)
-ref = ctx.icp_run(prm, T0)
-# sharded
-lo, hi = init_sharded(ctx, dist, len(pts), device=torch.device("cuda", local))
-ctx.set_source(pts[lo:hi])
-ctx.set_global_source_count(len(pts))
-res = ctx.icp_run(prm, T0)
-dT = np.abs(res.T - ref.T).max()
-ok = res.iterations == ref.iterations and dT < 1e-9 and all(
-    a.n_effective == b.n_effective and abs(a.fitness - b.fitness) < 1e-12 for a, b in zip(res.logs, ref.logs))
-t = torch.tensor([1.0 if ok else 0.0], device="cuda")
-dist.all_reduce(t, op=dist.ReduceOp.MIN)
+all_ok = True
+for method in ("Ours", "ME-TSVD"):
+    det, hand = ("SCHUR_CONDITION_NUMBER", "PRECONDITIONED_CG") if method == "Ours" else ("FULL_EVD_MIN_EIGENVALUE", "TRUNCATED_SVD")
+    prm = default_params(max_iterations=30, fixed_iterations=1, kappa_target=10.0, detection=det, handling=hand)   # long enough to reach the record-reusing mode
+    ref_ctx = Context(local)
+    ref_ctx.set_target(pts, 1.0)
+    ref_ctx.set_source(pts)
+    ref = ref_ctx.icp_run(prm, T0)                                         # single-GPU reference on every rank
+    planes, _ = ref_ctx.find_planes(T0, 1.0)
+    ref_ctx.freeze_planes_f32()
+    ref27, refstats = ref_ctx.reduce_device(True, T0, False)
+    for want_mode in (2, 1):
+        if want_mode == 1:
+            os.environ["DCREG_NO_PEER"] = "1"
+        else:
+            os.environ.pop("DCREG_NO_PEER", None)
+        ctx = Context(local)
+        ctx.set_target(pts, 1.0)
+        lo, hi = init_sharded(ctx, dist, len(pts), device=dev)
+        mode = ctx.comm_mode
+        ctx.set_source(pts[lo:hi])
+        ctx.set_global_source_count(len(pts))
+        res = ctx.icp_run(prm, T0)
+        res_b = ctx.icp_run(prm, T0)                                       # again: graph replay / epoch counters keep working
+        dT = np.abs(res.T - ref.T).max()
+        ok = res.iterations == ref.iterations and dT < 1e-9 and np.array_equal(res.T, res_b.T) and all(
+            a.n_effective == b.n_effective and a.n_corr_pt == b.n_corr_pt and abs(a.fitness - b.fitness) < 1e-12
+            for a, b in zip(res.logs, ref.logs))
+        # the K1 seam on the shard (planes of the shard from the unsharded run)
+        s27, sstats = ctx.reduce_normal_equations(np.concatenate([pts[lo:hi], np.zeros((hi - lo, 1), np.float32)], axis=1),
+                                                  planes[lo:hi], T0, False)
+        ok = ok and np.max(np.abs(s27 - ref27)) <= 1e-11 * np.max(np.abs(ref27)) and int(sstats[1]) == int(refstats[1])
+        t = torch.tensor([1.0 if ok else 0.0], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        tp = torch.from_numpy(np.concatenate([res.T.reshape(-1), s27])).to(dev)
+        tlo_, thi_ = tp.clone(), tp.clone()
+        dist.all_reduce(tlo_, op=dist.ReduceOp.MIN); dist.all_reduce(thi_, op=dist.ReduceOp.MAX)
+        same_bits = bool(torch.equal(tlo_, thi_))
+        if rank == 0:
+            print(f"{method} wanted mode {want_mode} got {mode}: max |T_sharded - T_single| = {dT:.3e}, identical over ranks: {same_bits}",
+                  "OK" if t.item() == 1.0 else "MISMATCH")
+        all_ok = all_ok and t.item() == 1.0 and (same_bits or mode != 2)
+        ctx.close()
+    ref_ctx.close()
 if rank == 0:
-    print("max |T_sharded - T_single| =", dT, "SHARDED_OK" if t.item() == 1.0 else "SHARDED_MISMATCH")
-ctx.close()
+    print("SHARDED_OK" if all_ok else "SHARDED_MISMATCH")
 dist.destroy_process_group()
-sys.exit(0 if t.item() == 1.0 else 1)
+sys.exit(0 if all_ok else 1)
