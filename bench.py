@@ -456,8 +456,8 @@ def run_ours(args, rank, local_rank, world):
     # ---------------- parity of the benchmarked configuration + CPU baseline (rank 0) ----------------
     cpu, parity = None, None
     if rank == 0 and not args.no_cpu_baseline:
+        arm = CpuArm(seed=42)                                                # rank 0's scene (puts oracle/ on sys.path)
         import dcreg_oracle as onp                                           # se3 log distance (NumPy twin)
-        arm = CpuArm(seed=42)                                                # rank 0's scene
         arm.calibrate()
         n_cpu_steps = 8 if world == 1 else 1
         times, T_cpu = arm.steps(n_cpu_steps, 1)

@@ -631,7 +631,7 @@ __global__ void init_state_kernel(IcpState* states, const double* T, long long n
     st->iter = 0; st->done = 0; st->converged = 0; st->status = DCREG_OK;
     for (int i = 0; i < 36; ++i) st->H_last[i] = (i % 7 == 0) ? 1.0 : 0.0;
     st->n_source_total = n_total;
-    st->step_rot = 1.0e30; st->step_trans = 1.0e30; st->seeds = 0; st->coherent_used = 0; st->coherent = 0; st->pad0 = 0;
+    st->step_rot = 1.0e30; st->step_trans = 1.0e30; st->seeds = 0; st->coherent_used = 0; st->coherent = 0; st->warm = 0;
     st->t_last = k2::globaltimer_ns();                      // tic of iteration 0 (icp_test_runner.cpp:1695)
     counters[b] = 0u;
 }

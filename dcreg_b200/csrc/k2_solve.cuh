@@ -11,6 +11,7 @@
 #pragma once
 #include "../../include/dcreg_b200.h"
 #include "small_la.cuh"
+#include "k2_fast.cuh"
 
 namespace k2 {
 
@@ -36,8 +37,9 @@ struct IcpState {               // device-resident loop state, written only by K
     int seeds;                  // 1: the iteration kernel that just ran left neighbour records behind
     int coherent_used;          // mode the iteration kernel that just ran was in (it reads it from `coherent`)
     int coherent;               // 1: the next iteration may use the records (the last update was small)
-    int pad0;
+    int warm;                   // 1: V_warm holds the Schur eigenvectors of the previous iteration (k2_fast.cuh)
     unsigned long long t_last;  // globaltimer (ns) at the end of the previous solve step / at run start (iter_time_ms)
+    double V_warm[2][9];        // [0] rotation block, [1] translation block, eigenvectors in columns
 };
 
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
@@ -486,6 +488,7 @@ struct WarpSmem {
     double dx[6];
     double Rt[12];           // pose copy: boxplus works on shared memory, lanes write it back in parallel
     double ilam[2][3];       // 1 / clamped Schur eigenvalues (preconditioner)
+    double Vw[2][9];         // warm-start bases (previous iteration's Schur eigenvectors), fetched with the first loads
     int ok[2];
 };
 
@@ -513,16 +516,17 @@ __device__ __forceinline__ int pcg6_warp(const WarpSmem& sm, int lane, int max_i
     double p = z;
     double rz = warp_sum(r * z);
     int it;
+    const double tol2 = tol * tol;                           // ||r|| < tol  <=>  ||r||^2 < tol^2: no square root on the chain
     for (it = 1; it <= max_iter; ++it) {
         const double Hp = row_dot_bcast(Hrow, p);
-        const double alpha = rz / warp_sum(p * Hp);
+        const double alpha = k2f::fast_div(rz, warp_sum(p * Hp));
         x = fma(alpha, p, x);
         r = fma(-alpha, Hp, r);
-        const double rn = sqrt(warp_sum(r * r));
-        if (rn < tol) break;                                 // identical in every lane: uniform branch
+        const double rn2 = warp_sum(r * r);
+        if (rn2 < tol2) break;                               // identical in every lane: uniform branch
         z = row_dot_bcast(Prow, r);
         const double rz_new = warp_sum(r * z);
-        p = fma(rz_new / rz, p, z);
+        p = fma(k2f::fast_div(rz_new, rz), p, z);
         rz = rz_new;
     }
     x_out = x;
@@ -543,6 +547,11 @@ __device__ inline void icp_step_warp_ours(const double* acc, IcpState* st, const
     }
     if (lane < 6) sm.g[lane] = acc[21 + lane];
     if (lane >= 8 && lane < 20) sm.Rt[lane - 8] = lane < 17 ? st->R[lane - 8] : st->t[lane - 17];
+    {   // warm start of the two Jacobi iterations (k2_fast.cuh); a cold start every 64 iterations bounds the drift of the
+        // accumulated rotations (5000-iteration runs, icp_iter.yaml)
+        const bool warm = st->warm != 0 && (iter & 63) != 0;
+        if (lane < 18) sm.Vw[lane / 9][lane % 9] = warm ? st->V_warm[lane / 9][lane % 9] : ((lane % 9) % 4 == 0 ? 1.0 : 0.0);
+    }
     if (rec) {
         if (lane < 27) rec->H27[lane] = acc[lane];
         if (lane == 0) { rec->iter = iter; rec->n_effective = n_eff; rec->n_corr_pt = n_pt; rec->status = DCREG_OK; }
@@ -569,9 +578,11 @@ __device__ inline void icp_step_warp_ours(const double* acc, IcpState* st, const
     if (lane < 2) {
         double M[9];
         const int o = lane == 0 ? 3 : 0;                     // lane 0: H_tt, lane 1: H_RR
+#pragma unroll
         for (int i = 0; i < 3; ++i)
+#pragma unroll
             for (int j = 0; j < 3; ++j) M[i * 3 + j] = sm.H[(i + o) * 6 + j + o];
-        sm.ok[lane] = dla::fullpiv_inverse<3>(M, sm.inv[lane]) ? 1 : 0;
+        sm.ok[lane] = k2f::spd_inverse3(M, sm.inv[lane]) ? 1 : 0;   // FullPivLU::isInvertible + inverse (k2_fast.cuh)
     }
     __syncwarp();
     const bool schur_ok = sm.ok[0] && sm.ok[1];
@@ -603,7 +614,17 @@ __device__ inline void icp_step_warp_ours(const double* acc, IcpState* st, const
         __syncwarp();
         if (lane < 18) sm.S[lane / 9][lane % 9] = sval;
         __syncwarp();
-        if (lane < 2) dla::jacobi_eigh3(sm.S[lane], sm.lam[lane], sm.V[lane]);
+        if (lane < 2) {
+            double Vw[9], Vn[9], ln[3], Sl[9];
+#pragma unroll
+            for (int e = 0; e < 9; ++e) { Sl[e] = sm.S[lane][e]; Vw[e] = sm.Vw[lane][e]; }
+            k2f::jacobi_eigh3_warm(Sl, Vw, ln, Vn);
+#pragma unroll
+            for (int e = 0; e < 9; ++e) { sm.V[lane][e] = Vn[e]; st->V_warm[lane][e] = Vn[e]; }
+#pragma unroll
+            for (int e = 0; e < 3; ++e) sm.lam[lane][e] = ln[e];
+            if (lane == 0) st->warm = 1;
+        }
         __syncwarp();
         // ---- detection (Eq. 20-21) and preconditioner (Eq. 43-46) ----
         bool deg = false;

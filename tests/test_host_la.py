@@ -20,3 +20,17 @@ def test_register_qr_is_bit_identical_to_the_generic_qr(tmp_path):
     res = subprocess.run([str(exe)], capture_output=True, text=True)
     assert res.returncode == 0, res.stdout + res.stderr
     assert "400000 systems, 0 mismatches" in res.stdout
+
+
+def test_fast_solve_step_pieces_on_the_host(tmp_path):
+    """k2_fast.cuh (warm-started 3x3 Jacobi, pivoted L D L^T inverse with the FullPivLU invertibility decision) compiled
+    as host code: residuals, orthogonality, warm == cold to rounding, decisions against a plain full-pivot LU."""
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    exe = tmp_path / "test_k2_fast"
+    subprocess.run([nvcc, "-O2", "-o", str(exe), os.path.join(ROOT, "tools", "test_k2_fast.cu")], check=True,
+                   capture_output=True, text=True)
+    res = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert "K2_FAST_OK" in res.stdout
