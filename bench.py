@@ -132,9 +132,16 @@ def workload_config(world):
             "roofline_workload": f"C4 synthetic corridor {C4_SLOTS} slots, frozen float4 planes"}
 
 
+_BUDGET = None
+
+
 def host_cpu_budget():
     """CPUs this process may really use: the affinity mask, capped by the cgroup CPU quota when there is one.
-    Returns (usable, affinity, quota or None)."""
+    Returns (usable, affinity, quota or None).  Evaluated once, BEFORE libgomp exists in the process: with
+    OMP_PROC_BIND set libgomp pins the initial thread to its first place and the mask would read 2."""
+    global _BUDGET
+    if _BUDGET is not None:
+        return _BUDGET
     aff = len(os.sched_getaffinity(0))
     quota = None
     try:                                               # cgroup v2
@@ -152,7 +159,8 @@ def host_cpu_budget():
         except Exception:
             pass
     usable = aff if quota is None else max(1, min(aff, int(quota + 0.5)))
-    return usable, aff, quota
+    _BUDGET = (usable, aff, quota)
+    return _BUDGET
 
 
 def pin_openmp_env(threads):
@@ -237,6 +245,62 @@ class CpuArm:
                 "host": {"affinity_cpus": self.aff, "cgroup_quota_cpus": self.quota, "usable_cpus": self.usable,
                          "omp": {k: os.environ.get(k) for k in ("OMP_PROC_BIND", "OMP_PLACES", "OMP_WAIT_POLICY")}},
                 "thread_calibration": self.calibration}
+
+
+def cpu_worker(args):
+    """`bench.py --cpu-worker`: everything the GPU arm wants from the host cores, in a CLEAN process (no torch, no CUDA
+    threads, same OpenMP set-up as `--impl reference`): the C2 cpu_baseline with the oracle's final pose (parity of the
+    benchmarked step), and for C5 the oracle's results of the first 16 trials plus an all-cores trials/s sample."""
+    arm = CpuArm(seed=42)
+    arm.calibrate()
+    times, T_cpu = arm.steps(args.steps, 1)
+    cpu = arm.describe(times)
+    cpu["reference_faithful_8_threads"] = arm.faithful()
+    from dcreg_b200.scenes import load_pcd_xyz, trial_poses
+    cyl = load_pcd_xyz(os.path.join(ROOT, "tests", "golden", "cylinder_7562.pcd"))
+    poses = trial_poses(C5_TRIALS, seed=45)
+    sc = arm.oc.Scene(cyl, cyl)
+    prm5 = arm.oc.make_params(max_iterations=30, kappa_target=10.0, n_threads=min(8, arm.usable))
+    ref5 = []
+    for k in range(16):
+        st5, conv5, it5, T5, _ = sc.icp_run(prm5, poses[k], want_log=False)
+        ref5.append({"status": int(st5), "converged": bool(conv5), "iterations": int(it5), "T": T5.reshape(-1).tolist()})
+    c5_cpu = None
+    if args.cpu_trials:
+        # independent trials: one single-threaded oracle registration per worker thread, all usable CPUs busy.  The
+        # workers drop the core binding the initial thread got from OMP_PROC_BIND.
+        from concurrent.futures import ThreadPoolExecutor
+        workers = int(arm.usable)
+        everything = set(range(os.cpu_count() or 1))
+        n5 = int(min(C5_TRIALS, max(4 * workers, 64)))
+        prm51 = arm.oc.make_params(max_iterations=30, kappa_target=10.0, n_threads=1)
+        scenes5 = [arm.oc.Scene(cyl, cyl) for _ in range(workers)]
+
+        def one(k):
+            try:
+                os.sched_setaffinity(0, everything)
+            except OSError:
+                pass
+            return scenes5[k % workers].icp_run(prm51, poses[k], want_log=False)[2]
+        with ThreadPoolExecutor(workers) as ex:
+            list(ex.map(one, range(workers)))                                # spin up
+            t5 = time.perf_counter()
+            list(ex.map(one, range(n5)))
+            t5 = time.perf_counter() - t5
+        pool_rate = n5 / t5
+        # ... or one registration at a time with the OpenMP team inside it (the reference's own arrangement)
+        prm5t = arm.oc.make_params(max_iterations=30, kappa_target=10.0, n_threads=arm.threads)
+        sc.icp_run(prm5t, poses[0], want_log=False)
+        n5s = 48
+        t5s = time.perf_counter()
+        for k in range(n5s):
+            sc.icp_run(prm5t, poses[k], want_log=False)
+        t5s = time.perf_counter() - t5s
+        seq_rate = n5s / t5s
+        c5_cpu = {"trials_per_s": max(pool_rate, seq_rate), "workers": workers,
+                  "modes": {"one_single_threaded_registration_per_worker": pool_rate, "sequential_registrations_openmp_inside": seq_rate},
+                  "sample": f"{n5} (pool) / {n5s} (sequential, {arm.threads} OpenMP threads) of the {C5_TRIALS} trials; the faster arrangement is quoted"}
+    print(json.dumps({"cpu_baseline": cpu, "c2_pose": T_cpu.reshape(-1).tolist(), "c5_ref": ref5, "c5_cpu": c5_cpu}))
 
 
 def run_reference(args, rank, world):
@@ -454,47 +518,35 @@ def run_ours(args, rank, local_rank, world):
     ctx2.close()
 
     # ---------------- parity of the benchmarked configuration + CPU baseline (rank 0) ----------------
+    # the host side runs in a clean subprocess (see cpu_worker), after every GPU-timed region
     cpu, parity = None, None
     if rank == 0 and not args.no_cpu_baseline:
-        arm = CpuArm(seed=42)                                                # rank 0's scene (puts oracle/ on sys.path)
-        import dcreg_oracle as onp                                           # se3 log distance (NumPy twin)
-        arm.calibrate()
-        n_cpu_steps = 8 if world == 1 else 1
-        times, T_cpu = arm.steps(n_cpu_steps, 1)
-        pose_err = float(onp.se3_log_distance(T_cpu, res.T))
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import dcreg_oracle as onp                                           # se3 log distance (NumPy twin), checker only
+        env = {k: v for k, v in os.environ.items() if not k.startswith("OMP_") and k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE")}
+        cmd = [sys.executable, os.path.abspath(__file__), "--cpu-worker", "--steps", "8" if world == 1 else "1"]
+        if world == 1:
+            cmd.append("--cpu-trials")
+        out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=900)
+        if out.returncode != 0:
+            raise SystemExit("bench.py: the CPU worker failed:\n" + out.stderr[-2000:])
+        host = json.loads(out.stdout.strip().splitlines()[-1])
+        pose_err = float(onp.se3_log_distance(np.array(host["c2_pose"]).reshape(4, 4), res.T))
         parity = {"parity_checked": True, "pose_err": pose_err, "tolerance": 1e-6,
                   "what": "|log(T_oracle^-1 T_gpu)| after the 50 fixed iterations of the timed C2 step, C/OpenMP oracle vs the e2e GPU result"}
         if not pose_err < 1e-6:
             raise SystemExit(f"bench.py: C2 parity FAILED, pose error {pose_err:.3e} vs the CPU oracle")
-        # C5 parity: a 16-trial sample of rank 0's trials against the C oracle
-        cyl_sc = arm.oc.Scene(cyl, cyl)
-        prm5c = arm.oc.make_params(max_iterations=30, kappa_target=10.0, n_threads=min(8, arm.usable))
         worst5 = 0.0
-        for k in range(0, 16):
-            st5, conv5, it5, T5, _ = cyl_sc.icp_run(prm5c, poses[tlo + k], want_log=False)
-            if st5 != trials[k].status or it5 != trials[k].iterations or conv5 != trials[k].converged:
+        for k, r5 in enumerate(host["c5_ref"]):
+            if r5["status"] != trials[k].status or r5["iterations"] != trials[k].iterations or r5["converged"] != trials[k].converged:
                 raise SystemExit(f"bench.py: C5 trial {k} differs from the CPU oracle (status/iterations/converged)")
-            worst5 = max(worst5, float(onp.se3_log_distance(T5, trials[k].T)))
+            worst5 = max(worst5, float(onp.se3_log_distance(np.array(r5["T"]).reshape(4, 4), trials[k].T)))
         if not worst5 < 1e-6:
             raise SystemExit(f"bench.py: C5 parity FAILED, pose error {worst5:.3e}")
-        c5["parity"] = {"trials_checked": 16, "max_pose_err": worst5, "tolerance": 1e-6}
+        c5["parity"] = {"trials_checked": len(host["c5_ref"]), "max_pose_err": worst5, "tolerance": 1e-6}
         if world == 1:
-            cpu = arm.describe(times)
-            cpu["reference_faithful_8_threads"] = arm.faithful()
-            # C5 on the CPU: independent trials, one single-threaded oracle run per worker thread, all usable CPUs busy
-            from concurrent.futures import ThreadPoolExecutor
-            n5 = int(min(C5_TRIALS, max(2 * arm.threads, 64)))
-            prm51 = arm.oc.make_params(max_iterations=30, kappa_target=10.0, n_threads=1)
-            scenes5 = [arm.oc.Scene(cyl, cyl) for _ in range(arm.threads)]
-            def one(k):
-                return scenes5[k % arm.threads].icp_run(prm51, poses[k], want_log=False)[2]
-            with ThreadPoolExecutor(arm.threads) as ex:
-                list(ex.map(one, range(arm.threads)))                        # spin up
-                t5 = time.perf_counter()
-                list(ex.map(one, range(n5)))
-                t5 = time.perf_counter() - t5
-            c5["cpu_port"] = {"trials_per_s": n5 / t5, "workers": int(arm.threads), "sample": f"{n5} of the {C5_TRIALS} trials, "
-                              "one single-threaded oracle registration per worker thread"}
+            cpu = host["cpu_baseline"]
+            c5["cpu_port"] = host["c5_cpu"]
 
     if rank == 0:
         line = {
@@ -541,10 +593,16 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-worker", action="store_true", help=argparse.SUPPRESS)
+    ap.add_argument("--cpu-trials", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
     rank, local_rank, world = env_int("RANK", 0), env_int("LOCAL_RANK", 0), env_int("WORLD_SIZE", 1)
-    pin_openmp_env(host_cpu_budget()[0])       # before anything loads libgomp (torch does): see pin_openmp_env
+    if args.cpu_worker:
+        pin_openmp_env(host_cpu_budget()[0])
+        cpu_worker(args)
+        return
     if args.impl == "reference":
+        pin_openmp_env(host_cpu_budget()[0])   # before anything loads libgomp: see pin_openmp_env
         run_reference(args, rank, world)
     else:
         run_ours(args, rank, local_rank, world)

@@ -89,7 +89,7 @@ EXPORTS = [
     "dcreg_reduce_normal_equations_host", "dcreg_analyze_and_solve", "dcreg_solve_pcg", "dcreg_icp_run",
     "dcreg_icp_run_batch", "dcreg_icp_run_host_planes", "dcreg_comm_mode", "dcreg_last_covariance", "dcreg_point_to_point_metrics", "dcreg_comm_unique_id", "dcreg_comm_init",
     "dcreg_comm_destroy", "dcreg_set_global_source_count", "dcreg_launch_count", "dcreg_device_source",
-    "dcreg_device_planes_f64", "dcreg_device_planes_f32", "dcreg_freeze_planes_f32", "dcreg_time_reduce", "dcreg_time_iteration", "dcreg_iteration_counters",
+    "dcreg_device_planes_f64", "dcreg_device_planes_f32", "dcreg_freeze_planes_f32", "dcreg_time_reduce", "dcreg_time_iteration", "dcreg_iteration_counters", "dcreg_iteration_timeline",
 ]
 
 
@@ -138,6 +138,7 @@ def load_library():
     lib.dcreg_time_reduce.argtypes = [vp, ci, dp, ci, ci, ci, C.POINTER(C.c_float)]
     lib.dcreg_time_iteration.argtypes = [vp, C.POINTER(IcpParams), dp, ci, ci, C.POINTER(C.c_float)]
     lib.dcreg_iteration_counters.argtypes = [vp, ci, C.POINTER(C.c_uint64)]
+    lib.dcreg_iteration_timeline.argtypes = [vp, C.POINTER(IcpParams), dp, ci, C.POINTER(C.c_uint64), ci, C.POINTER(ci)]
     _lib = lib
     return lib
 
@@ -290,6 +291,16 @@ class Context:
         T = np.ascontiguousarray(T, dtype=np.float64)
         self._check(self.lib.dcreg_time_iteration(self._h, C.byref(params), _dptr(T), int(what), int(reps), C.byref(ms)))
         return float(ms.value)
+
+    def iteration_timeline(self, params: IcpParams, T, iters: int):
+        """Phase time stamps (ns) of the last of `iters` real iterations from pose T: (blocks (n, 16), solve (16,))."""
+        T = np.ascontiguousarray(T, dtype=np.float64)
+        cap = 4096
+        out = np.zeros((cap, 16), dtype=np.uint64)
+        nb = C.c_int(0)
+        self._check(self.lib.dcreg_iteration_timeline(self._h, C.byref(params), _dptr(T), int(iters),
+                                                      out.ctypes.data_as(C.POINTER(C.c_uint64)), cap, C.byref(nb)))
+        return out[:nb.value].astype(np.int64), out[nb.value].astype(np.int64)
 
     def iteration_counters(self, enable: bool = True):
         out = (C.c_uint64 * 2)()

@@ -484,6 +484,7 @@ constexpr int kWarpKnnCap = 64;
 
 struct WarpKnnSmem {
     int rs[81], re[81];                              // point range per cell row (empty when pruned)
+    int pref[82];                                    // exclusive prefix sums of the row lengths (+ total)
     float d2[kWarpKnnCap];
     int pos[kWarpKnnCap], idx[kWarpKnnCap];
     float od2[kSeeds];
@@ -540,27 +541,58 @@ __device__ __forceinline__ bool knn_warp_search(const Grid& g, float qx, float q
         S.rs[r] = s; S.re[r] = e;
     }
     __syncwarp();
+    // Candidates of ALL rows as one flat list (prefix sums of the row lengths): lane l takes candidates l, l + 32, ...
+    // wherever their rows are, so the point loads of different rows are independent and in flight together (walking
+    // the rows one after the other costs one dependent memory round trip per row: 9 for cell = radius, up to 81).
+    int total = 0;
+#pragma unroll 1
+    for (int base = 0; base < nrows; base += 32) {
+        const int r = base + lane;
+        const int len = r < nrows ? S.re[r] - S.rs[r] : 0;
+        int incl = len;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const int t = __shfl_up_sync(full, incl, off);
+            if (lane >= off) incl += t;
+        }
+        if (r < nrows) S.pref[r] = total + incl - len;
+        total += __shfl_sync(full, incl, 31);
+    }
+    if (lane == 0) S.pref[nrows] = total;
+    __syncwarp();
     int cnt = 0;
     bool overflow = false;
+    int row = 0;                                      // row of this lane's current candidate (candidates ascend per lane)
 #pragma unroll 1
-    for (int r = 0; r < nrows; ++r) {
-        const int e = S.re[r];
-#pragma unroll 1
-        for (int j0 = S.rs[r]; j0 < e; j0 += 32) {
-            const int j = j0 + lane;
+    for (int c0 = 0; c0 < total; c0 += 64) {          // two candidates per lane and trip: both loads in flight
+        int jj[2];
+        bool in[2];
+        float4 pp[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int c = c0 + u * 32 + lane;
+            in[u] = c < total;
+            jj[u] = 0;
+            if (in[u]) {
+                while (c >= S.pref[row + 1]) ++row;
+                jj[u] = S.rs[row] + (c - S.pref[row]);
+                pp[u] = __ldg(&g.pts[jj[u]]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
             bool hit = false;
             float d = 0.0f;
             int pi = 0;
-            if (j < e) {
-                const float4 p = __ldg(&g.pts[j]);
-                d = dist2(qx, qy, qz, p);
-                pi = __float_as_int(p.w);
+            if (in[u]) {
+                d = dist2(qx, qy, qz, pp[u]);
+                pi = __float_as_int(pp[u].w);
                 hit = d <= B;
                 if (!hit) lbl = fminf(lbl, d);
             }
             const unsigned bits = __ballot_sync(full, hit);
             const int slot = cnt + __popc(bits & ((1u << lane) - 1u));
-            if (hit && slot < kWarpKnnCap) { S.d2[slot] = d; S.pos[slot] = j; S.idx[slot] = pi; }
+            if (hit && slot < kWarpKnnCap) { S.d2[slot] = d; S.pos[slot] = jj[u]; S.idx[slot] = pi; }
             cnt += __popc(bits);
         }
         if (cnt > kWarpKnnCap) { overflow = true; break; }

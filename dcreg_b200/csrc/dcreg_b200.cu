@@ -71,16 +71,17 @@ __device__ __forceinline__ bool last_block_ticket(unsigned int* counter) {
 // own register allocation and stack frame: the iteration kernels are capped at 85 registers for 3 blocks per SM and
 // must not pay for the solve's live state.  acc: the body-frame sums in shared memory.
 static_assert(sizeof(k2::WarpSmem) <= 8 * k1::kTRow * sizeof(double), "k2::WarpSmem must fit one warp's transpose buffer");
+static_assert(sizeof(corr::WarpKnnSmem) <= 8 * k1::kTRow * sizeof(double), "corr::WarpKnnSmem must fit one warp's transpose buffer");
 __device__ __noinline__ void solve_step_in_kernel(const double* acc, IcpState* st, const dcreg_icp_params* prm,
                                                   dcreg_iter_log* log, int log_cap, k2::WarpSmem* sm, const float* src_radius,
-                                                  double coherent_step, unsigned int* n_active) {
+                                                  double coherent_step, unsigned int* n_active, unsigned long long* dbg) {
     // only the "Ours" method (Schur detection + PCG, the warp-cooperative step) is folded; the baseline methods' generic
     // single-thread step needs a 3.7 KB stack frame, which every thread of the iteration kernel would have to reserve:
     // they keep the separate solve kernel (k2_step_kernel)
     const int lane = threadIdx.x & 31;
     const double lever = src_radius ? (double)*src_radius : 1.0e30;
     const double max_step = coherent_step * prm->search_radius;
-    k2::icp_step_warp_ours(acc, st, *prm, log, log_cap, *sm, lever, max_step);         // all 32 lanes cooperate
+    k2::icp_step_warp_ours(acc, st, *prm, log, log_cap, *sm, lever, max_step, dbg);    // all 32 lanes cooperate
     __syncwarp();
     if (lane == 0 && n_active && st->done) atomicSub(n_active, 1u);
 }
@@ -167,6 +168,9 @@ constexpr int kNnRec = 3;
 constexpr float kNnLook = 1.21f;              // squared-distance look-ahead beyond the seed bound (any value >= 1 is exact)
 constexpr double kCoherentStep = 0.05;        // records are used once no source point moves more than this x search radius per iteration
 
+constexpr int kStampSlots = 16;                // per-block phase time stamps of the loop kernel (profiling only)
+#define DCREG_STAMP(k) do { if (a.stamps && tid == 0) a.stamps[(size_t)blockIdx.x * kStampSlots + (k)] = k2::globaltimer_ns(); } while (0)
+
 constexpr int kSearchListMax = 96;            // more searching slots than this in a 256-slot tile: every thread searches for itself
 
 struct Iter2Smem {
@@ -201,6 +205,7 @@ struct Iter2Args {
     double coherent_step;
     unsigned int* n_active;   // trials still running (decremented by the step that finishes one); host polls it
     peer::View peer;          // multi-GPU: the sum over ranks, inside the last block (peer_reduce.cuh)
+    unsigned long long* stamps;   // profiling only (dcreg_iteration_timeline): [grid.x][kStampSlots] globaltimer values, or null
     int coop_max;             // more searching slots than this in a tile: every thread searches for itself (kSearchListMax)
     int force;                // 0: mode and seeds from the loop state (written by K2); 1: coherent mode, seeds = use_seeds
     int use_seeds;            // (force) records of the previous launch are valid
@@ -230,6 +235,7 @@ __global__ void __launch_bounds__(kBlock, 3) icp_iter2_kernel(const __grid_const
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const k1::Pose P = load_pose(st);
     const corr::Grid& g = A.grid;
+    DCREG_STAMP(0);
     // this trial's slices of the per-slot records
     int4* const rec_nn = a.nn + (size_t)trial * kNnRec * A.n;
     double4* const rec_plane = a.plane_cache + (size_t)trial * A.n;
@@ -306,6 +312,7 @@ __global__ void __launch_bounds__(kBlock, 3) icp_iter2_kernel(const __grid_const
                 wbase = __shfl_sync(0xffffffffu, wbase, 0);
                 if (need) sm.listS[wbase + __popc(bits & ((1u << lane) - 1u))] = tid;
             }
+            DCREG_STAMP(1);
             __syncthreads();
             // -- 2. searches: few -> one warp per listed slot (the other slots' threads are not held up by a
             //       15 us sequential search); many -> every thread searches for its own slot
@@ -328,6 +335,7 @@ __global__ void __launch_bounds__(kBlock, 3) icp_iter2_kernel(const __grid_const
                 }
                 __syncthreads();
             }
+            DCREG_STAMP(2);
             if (valid && sm.res[tid][9] == 2) {       // too many for the list, or more than 64 candidates inside the bound
                 const float4 q = sm.q[tid];
                 if (coherent) {
@@ -399,6 +407,7 @@ __global__ void __launch_bounds__(kBlock, 3) icp_iter2_kernel(const __grid_const
                 wbase = __shfl_sync(0xffffffffu, wbase, 0);
                 if (want_fit) sm.listF[wbase + __popc(bits & ((1u << lane) - 1u))] = tid;
             }
+            DCREG_STAMP(3);
             __syncthreads();
             // -- 3b. fits, densely packed into the first warps
             const int nF = sm.nF;
@@ -422,6 +431,7 @@ __global__ void __launch_bounds__(kBlock, 3) icp_iter2_kernel(const __grid_const
                 ++n_fit;
             }
             __syncthreads();
+            DCREG_STAMP(4);
             // -- 3c. gate, row, Gram
             if (valid) {
                 if (want_fit) {
@@ -440,6 +450,7 @@ __global__ void __launch_bounds__(kBlock, 3) icp_iter2_kernel(const __grid_const
             __syncthreads();
         }
     }
+    DCREG_STAMP(5);
     if (a.stats) {
         n_search = __reduce_add_sync(0xffffffffu, n_search);
         n_fit = __reduce_add_sync(0xffffffffu, n_fit);
@@ -471,13 +482,19 @@ __global__ void __launch_bounds__(kBlock, 3) icp_iter2_kernel(const __grid_const
     // ---- grid reduction of this trial, [sum over ranks], congruence, solve + pose update: all in the last block
     if (!k1s::reduce_to_fin(mine, sm.tail, A.partials + (size_t)trial * gridDim.x * k1s::kPk, A.counter + trial,
                             (int)blockIdx.x, (int)gridDim.x)) return;
+    DCREG_STAMP(6);
     peer::all_reduce32(a.peer, sm.tail.fin, sm.tail.red);
     k1s::congruence(sm.tail.fin, st->R, sm.tail.acc);
     __syncthreads();
+    DCREG_STAMP(7);
     if (tid < kAcc) A.acc[(size_t)trial * kAcc + tid] = sm.tail.acc[tid];
-    if (a.fold_k2 && warp == 0)
+    if (a.fold_k2 && warp == 0) {
         solve_step_in_kernel(sm.tail.acc, st, &A.prm, a.log ? a.log + (size_t)trial * a.log_cap : nullptr, a.log_cap,
-                             reinterpret_cast<k2::WarpSmem*>(sm.tbuf[0]), a.src_radius, a.coherent_step, a.n_active);
+                             reinterpret_cast<k2::WarpSmem*>(sm.tbuf[0]), a.src_radius, a.coherent_step, a.n_active,
+                             a.stamps ? a.stamps + (size_t)gridDim.x * kStampSlots : nullptr);
+        DCREG_STAMP(8);
+        if (a.stamps && tid == 0) a.stamps[(size_t)gridDim.x * kStampSlots + 15] = blockIdx.x;      // which block was last
+    }
 }
 
 // K2 as its own kernel (seam 3, and the sharded loop after the all-reduce).
@@ -1583,6 +1600,38 @@ int dcreg_time_iteration(dcreg_ctx* ctx, const dcreg_icp_params* params, const d
     cudaEventDestroy(b0); cudaEventDestroy(b1);
     *ms_per_body = ms / reps;
     return DCREG_OK;
+}
+
+int dcreg_iteration_timeline(dcreg_ctx* ctx, const dcreg_icp_params* params, const double T[16], int iters, uint64_t* out,
+                             int out_cap_blocks, int* n_blocks) {
+    if (!ctx || !params || !T || iters < 1 || !out || !n_blocks) return DCREG_BAD_ARG;
+    if (!ctx->d_src || !ctx->has_grid) { ctx->err = "iteration_timeline: set source and target first"; return DCREG_BAD_ARG; }
+    CK(cudaSetDevice(ctx->device));
+    dcreg_icp_params prm = *params;
+    prm.fixed_iterations = 1;
+    prm.max_iterations = iters + 8;
+    int rc;
+    if ((rc = init_state(ctx, T))) return rc;
+    const float4* src_iter = ctx->d_src;
+    if ((rc = sort_source_by_cell(ctx, T, &src_iter))) return rc;
+    LoopPlan L;
+    if ((rc = plan_iteration(ctx, &prm, src_iter, nullptr, 1, nullptr, 0, true, &L))) return rc;
+    if (!L.fused2) { ctx->err = "iteration_timeline: needs the dense-grid loop kernel"; return DCREG_BAD_ARG; }
+    *n_blocks = L.grid_x;
+    if (out_cap_blocks < L.grid_x + 1) { ctx->err = "iteration_timeline: output too small"; return DCREG_BAD_ARG; }
+    const size_t bytes = (size_t)(L.grid_x + 1) * kStampSlots * sizeof(unsigned long long);
+    unsigned long long* d_st = nullptr;
+    CK(cudaMalloc(&d_st, bytes));
+    CK(cudaMemsetAsync(d_st, 0, bytes, ctx->stream));
+    for (int i = 0; i + 1 < iters && rc == DCREG_OK; ++i) rc = launch_body(ctx, L, &prm, nullptr, 0, true);
+    L.b.stamps = d_st;
+    if (rc == DCREG_OK) rc = launch_body(ctx, L, &prm, nullptr, 0, true);
+    if (rc == DCREG_OK) {
+        cudaMemcpyAsync(out, d_st, bytes, cudaMemcpyDeviceToHost, ctx->stream);
+        if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { ctx->err = "iteration_timeline: stream error"; rc = DCREG_CUDA_ERROR; }
+    }
+    cudaFree(d_st);
+    return rc;
 }
 
 int dcreg_analyze_and_solve(dcreg_ctx* ctx, const double H27[27], const dcreg_icp_params* params,

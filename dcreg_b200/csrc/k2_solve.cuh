@@ -534,9 +534,14 @@ __device__ __forceinline__ int pcg6_warp(const WarpSmem& sm, int lane, int max_i
 }
 
 // One K2 step by one warp.  Same observable behaviour as icp_step for the "Ours" method.
+// dbg (profiling only, may be null): globaltimer stamps [0] entry, [1] after the block inverses, [2] after the Schur
+// eigen-decompositions, [3] after the preconditioner, [4] after the solve, [5] after the pose update.
+#define K2_STAMP(k) do { if (dbg && lane == 0) dbg[k] = globaltimer_ns(); } while (0)
 __device__ inline void icp_step_warp_ours(const double* acc, IcpState* st, const dcreg_icp_params& prm,
-                                          dcreg_iter_log* log, int log_cap, WarpSmem& sm, double lever, double max_step) {
+                                          dcreg_iter_log* log, int log_cap, WarpSmem& sm, double lever, double max_step,
+                                          unsigned long long* dbg = nullptr) {
     const int lane = threadIdx.x & 31;
+    K2_STAMP(0);
     const int iter = st->iter;
     dcreg_iter_log* rec = (log != nullptr && iter < log_cap) ? &log[iter] : nullptr;
     const int n_eff = (int)(acc[kAccNeff] + 0.5);
@@ -585,6 +590,7 @@ __device__ inline void icp_step_warp_ours(const double* acc, IcpState* st, const
         sm.ok[lane] = k2f::spd_inverse3(M, sm.inv[lane]) ? 1 : 0;   // FullPivLU::isInvertible + inverse (k2_fast.cuh)
     }
     __syncwarp();
+    K2_STAMP(1);
     const bool schur_ok = sm.ok[0] && sm.ok[1];
     int degenerate = 0;
     if (schur_ok) {
@@ -626,6 +632,7 @@ __device__ inline void icp_step_warp_ours(const double* acc, IcpState* st, const
             if (lane == 0) st->warm = 1;
         }
         __syncwarp();
+        K2_STAMP(2);
         // ---- detection (Eq. 20-21) and preconditioner (Eq. 43-46) ----
         bool deg = false;
         if (lane < 6) {
@@ -652,6 +659,7 @@ __device__ inline void icp_step_warp_ours(const double* acc, IcpState* st, const
         }
         __syncwarp();
     }
+    K2_STAMP(3);
     // ---- solve ----
     if (degenerate) {
         if (lane < 8) {
@@ -663,6 +671,7 @@ __device__ inline void icp_step_warp_ours(const double* acc, IcpState* st, const
         qr6(sm.H, sm.g, sm.dx);                              // dcreg.hpp:190
     }
     __syncwarp();
+    K2_STAMP(4);
     const double dxi = lane < 6 ? sm.dx[lane] : 0.0;
     const bool finite = __ballot_sync(0xffffffffu, !isfinite(dxi)) == 0u;
     const double fitness = st->n_source_total > 0 ? (double)n_pt / (double)st->n_source_total : 0.0;
@@ -702,6 +711,7 @@ __device__ inline void icp_step_warp_ours(const double* acc, IcpState* st, const
         if (rec) rec->iter_time_ms = ms;
     }
     __syncwarp();
+    K2_STAMP(5);
     if (lane < 9) st->R[lane] = sm.Rt[lane];
     else if (lane < 12) st->t[lane - 9] = sm.Rt[lane];
     if (rec) {

@@ -207,9 +207,10 @@ int dcreg_icp_run(dcreg_ctx* ctx, const dcreg_icp_params* params, const double T
  * (icp_test_runner.cpp:331-345: `for run in 0..num_runs: runSingleTest`) and is what a perturbation Monte-Carlo
  * (BASELINE.json configs[4]) calls.  T_init / T_out: n_trials row-major 4x4 matrices; n_iterations / converged / status:
  * n_trials ints (status[t] = what dcreg_icp_run would have returned for trial t; any may be NULL except T_init, T_out);
- * log: n_trials x log_cap records (trial-major) or NULL.  Every trial's result is bit-identical to a dcreg_icp_run
- * with the same T_init (same kernels, same summation order).  Not available on a sharded context: trials are
- * independent, distribute them over ranks instead.  Needs the dense target grid. */
+ * log: n_trials x log_cap records (trial-major) or NULL.  Every trial runs the kernels a dcreg_icp_run from the same
+ * T_init runs: counts, masks and iteration counts are identical, poses equal up to the order of the FP64 sums (the
+ * source is sorted by target cell once, under trial 0's pose; trial 0 is bit-identical to its single run).  Not
+ * available on a sharded context: trials are independent, distribute them over ranks instead.  Needs the dense grid. */
 int dcreg_icp_run_batch(dcreg_ctx* ctx, const dcreg_icp_params* params, int n_trials, const double* T_init,
                         double* T_out, int* n_iterations, int* converged, int* status, dcreg_iter_log* log,
                         int log_cap);
@@ -266,6 +267,14 @@ int dcreg_time_reduce(dcreg_ctx* ctx, int plane_is_f64, const double pose_Rt[12]
  * pose T; what = 1: iteration kernel + solve/update kernel, i.e. `reps` real iterations (no convergence stop). */
 int dcreg_time_iteration(dcreg_ctx* ctx, const dcreg_icp_params* params, const double T[16], int what,
                          int reps, float* ms_per_body);
+/* Profiling aid: run `iters` real loop iterations from pose T and record the phase time stamps (GPU globaltimer, ns) of
+ * the LAST one.  out: (n_blocks + 1) x 16 values; row b < n_blocks, thread 0 of block b: [0] start (pose loaded),
+ * [1] certificates done, [2] searches done, [3] fit list built, [4] fits done, [5] rows / Gram done, and for the block
+ * that finished the reduction [6] partials summed, [7] sums ready, [8] solve step done; row n_blocks: the solve step's
+ * own stamps [0] entry, [1] block inverses, [2] Schur eigen-decompositions, [3] preconditioner, [4] solve, [5] pose
+ * update, and [15] = index of the block that ran it. */
+int dcreg_iteration_timeline(dcreg_ctx* ctx, const dcreg_icp_params* params, const double T[16], int iters,
+                             uint64_t* out, int out_cap_blocks, int* n_blocks);
 /* Profiling counters of the loop's iteration kernel since the last call: out = { source slots that ran a neighbour
  * search, source slots that ran a plane fit } (the others reused the previous iteration's result).
  * enable != 0 switches the counting on (off by default), 0 switches it off. */

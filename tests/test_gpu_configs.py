@@ -142,9 +142,11 @@ def perturbations(n, seed=45):
 
 
 @pytest.mark.parametrize("method", ["Ours", "ME-TSVD"])
-def test_batched_trials_equal_single_runs_bit_for_bit(ctx, cylinder, method):
-    """dcreg_icp_run_batch (icp_test_runner.cpp:331-345 side by side): every trial's pose, iteration count, flags and
-    log are IDENTICAL to a dcreg_icp_run from the same initial pose (same kernels, same summation order)."""
+def test_batched_trials_equal_single_runs(ctx, cylinder, method):
+    """dcreg_icp_run_batch (icp_test_runner.cpp:331-345 side by side): every trial runs the same kernels as a
+    dcreg_icp_run from the same initial pose - iteration counts, flags, per-iteration counts and masks identical, poses
+    equal to summation-order rounding (the source is sorted by target cell under the FIRST trial's pose, so only trial
+    0 adds its slots in exactly the order of its single run: that one is bit-identical)."""
     from dcreg_b200 import default_params
     det, hand = ("SCHUR_CONDITION_NUMBER", "PRECONDITIONED_CG") if method == "Ours" else ("FULL_EVD_MIN_EIGENVALUE", "TRUNCATED_SVD")
     gp = default_params(kappa_target=10.0, max_iterations=30, detection=det, handling=hand)
@@ -152,16 +154,20 @@ def test_batched_trials_equal_single_runs_bit_for_bit(ctx, cylinder, method):
     ctx.set_target(cylinder, 1.0)
     ctx.set_source(cylinder)
     batch = ctx.icp_run_batch(gp, Ts, want_log=True)
+    again = ctx.icp_run_batch(gp, Ts)
     assert len(batch) == 24
     n_conv = 0
-    for b, T0 in zip(batch, Ts):
+    for t, (b, T0) in enumerate(zip(batch, Ts)):
         single = ctx.icp_run(gp, T0)
         assert b.status == single.status and b.iterations == single.iterations and b.converged == single.converged
-        assert np.array_equal(b.T, single.T)
+        assert np.array_equal(b.T, again[t].T)                                # a batch is reproducible bit for bit
+        if t == 0:
+            assert np.array_equal(b.T, single.T)
+        assert o.se3_log_distance(single.T, b.T) < 1e-11
         assert len(b.logs) == len(single.logs)
         for x, y in zip(b.logs, single.logs):
             assert x.n_effective == y.n_effective and x.n_corr_pt == y.n_corr_pt
-            assert np.array_equal(np.array(x.dx), np.array(y.dx)) and np.array_equal(np.array(x.H27), np.array(y.H27))
+            assert rel_err(np.array(x.H27), np.array(y.H27)) < 1e-12 and np.max(np.abs(np.array(x.dx) - np.array(y.dx))) < 1e-11
             assert list(x.analysis.degenerate_mask) == list(y.analysis.degenerate_mask)
         n_conv += int(b.converged)
     assert n_conv >= 12                      # trials stop on their own convergence test

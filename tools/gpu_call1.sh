@@ -7,9 +7,13 @@ tail -5 gpurun_out/pytest.log
 timeout 300 python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/ref_a.json 2> gpurun_out/ref_a.err; echo "ref rc=$?"
 timeout 600 python bench.py --steps 20 --warmup 3 > gpurun_out/bench_a.json 2> gpurun_out/bench_a.err; echo "bench rc=$?"
 tail -c 600 gpurun_out/bench_a.err
-for v in default NO_GRAPH NO_FOLD NO_PDL; do
+for v in default NO_GRAPH NO_FOLD; do
   if [ $v = default ]; then VARIANT=$v timeout 200 python tools/loop_variants.py; else env VARIANT=$v DCREG_$v=1 timeout 200 python tools/loop_variants.py; fi
 done > gpurun_out/variants.log 2>&1
+env VARIANT=coherent_always_coop256 DCREG_COHERENT_STEP=1e9 DCREG_COOP_MAX=256 timeout 200 python tools/loop_variants.py >> gpurun_out/variants.log 2>&1
+env VARIANT=coherent_always_coop96 DCREG_COHERENT_STEP=1e9 timeout 200 python tools/loop_variants.py >> gpurun_out/variants.log 2>&1
+env VARIANT=coop256 DCREG_COOP_MAX=256 timeout 200 python tools/loop_variants.py >> gpurun_out/variants.log 2>&1
+env VARIANT=coop32 DCREG_COOP_MAX=32 timeout 200 python tools/loop_variants.py >> gpurun_out/variants.log 2>&1
 cat gpurun_out/variants.log | cut -c1-400
 timeout 300 python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/ref_b.json 2>> gpurun_out/ref_a.err
 python -c "
