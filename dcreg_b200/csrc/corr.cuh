@@ -564,12 +564,13 @@ __device__ __forceinline__ bool knn_warp_search(const Grid& g, float qx, float q
     bool overflow = false;
     int row = 0;                                      // row of this lane's current candidate (candidates ascend per lane)
 #pragma unroll 1
-    for (int c0 = 0; c0 < total; c0 += 64) {          // two candidates per lane and trip: both loads in flight
-        int jj[2];
-        bool in[2];
-        float4 pp[2];
+    constexpr int kU = 4;                             // candidates per lane and trip: that many loads in flight
+    for (int c0 = 0; c0 < total; c0 += 32 * kU) {
+        int jj[kU];
+        bool in[kU];
+        float4 pp[kU];
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
+        for (int u = 0; u < kU; ++u) {
             const int c = c0 + u * 32 + lane;
             in[u] = c < total;
             jj[u] = 0;
@@ -580,7 +581,7 @@ __device__ __forceinline__ bool knn_warp_search(const Grid& g, float qx, float q
             }
         }
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
+        for (int u = 0; u < kU; ++u) {
             bool hit = false;
             float d = 0.0f;
             int pi = 0;

