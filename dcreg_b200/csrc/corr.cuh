@@ -258,14 +258,18 @@ __device__ __forceinline__ float dist2(float qx, float qy, float qz, const float
 __device__ __forceinline__ void knn_scan_range(const float4* __restrict__ pts, int s, int e, float qx, float qy,
                                                float qz, Knn5& k) {
     int j = s;
-    for (; j + 1 < e; j += 2) {                       // two candidates per trip: both loads in flight
-        const float4 p0 = __ldg(&pts[j]), p1 = __ldg(&pts[j + 1]);
-        const float a0 = dist2(qx, qy, qz, p0), a1 = dist2(qx, qy, qz, p1);
-        const int i0 = __float_as_int(p0.w), i1 = __float_as_int(p1.w);
+#pragma unroll 1
+    for (; j + 3 < e; j += 4) {                       // four candidates per trip: four loads in flight (the scan is one
+        const float4 p0 = __ldg(&pts[j]), p1 = __ldg(&pts[j + 1]), p2 = __ldg(&pts[j + 2]), p3 = __ldg(&pts[j + 3]);   // thread's latency chain)
+        const float a0 = dist2(qx, qy, qz, p0), a1 = dist2(qx, qy, qz, p1), a2 = dist2(qx, qy, qz, p2), a3 = dist2(qx, qy, qz, p3);
+        const int i0 = __float_as_int(p0.w), i1 = __float_as_int(p1.w), i2 = __float_as_int(p2.w), i3 = __float_as_int(p3.w);
         if (a0 < k.d2[4] || (a0 == k.d2[4] && i0 < k.idx[4])) knn_insert(k, a0, j, i0);
         if (a1 < k.d2[4] || (a1 == k.d2[4] && i1 < k.idx[4])) knn_insert(k, a1, j + 1, i1);
+        if (a2 < k.d2[4] || (a2 == k.d2[4] && i2 < k.idx[4])) knn_insert(k, a2, j + 2, i2);
+        if (a3 < k.d2[4] || (a3 == k.d2[4] && i3 < k.idx[4])) knn_insert(k, a3, j + 3, i3);
     }
-    if (j < e) {
+#pragma unroll 1
+    for (; j < e; ++j) {
         const float4 p0 = __ldg(&pts[j]);
         const float a0 = dist2(qx, qy, qz, p0);
         const int i0 = __float_as_int(p0.w);
@@ -742,9 +746,11 @@ __device__ __forceinline__ bool fit_plane(const Grid& g, const int (&kpos)[5], d
     return worst < thickness * thickness;                // :1772-1773
 }
 
-// The same fit with the register-resident QR (small_la.cuh: same operations in the same order).  A separate function
-// with its own register allocation: it is called from the fit work list of the loop kernel, where almost nothing is
-// live across the call (inlined into a loop body full of live state it spills; measured 3.7x slower there).
+// The same fit with the register-resident QR (small_la.cuh: same operations in the same order, divisions and square roots
+// through the hardware seeds + Newton: a fit is ONE thread's dependent chain, 7 us of every loop iteration with the IEEE
+// sequences).  A separate function with its own register allocation: it is called from the fit work list of the loop
+// kernel, where almost nothing is live across the call (inlined into a loop body full of live state it spills; measured
+// 3.7x slower there).  A cached plane is reused only by the loop kernel itself, so reuse stays bit-identical to a refit.
 __device__ __noinline__ bool fit_plane_reg(const Grid& g, const int (&kpos)[5], double min_norm, double thickness,
                                            double& nx, double& ny, double& nz, double& d) {
     double A[5][3], b[5], x[3];
@@ -756,10 +762,12 @@ __device__ __noinline__ bool fit_plane_reg(const Grid& g, const int (&kpos)[5], 
         A[j][2] = (double)p.z;
         b[j] = -1.0;
     }
-    dla::colpiv_qr_solve_reg<5, 3>(A, b, x);
-    const double ps = sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
-    if (!(ps >= min_norm)) return false;                 // :1752 (also rejects NaN)
-    nx = x[0] / ps; ny = x[1] / ps; nz = x[2] / ps; d = 1.0 / ps;
+    dla::colpiv_qr_solve_reg<5, 3, true>(A, b, x);
+    const double ps2 = x[0] * x[0] + x[1] * x[1] + x[2] * x[2];
+    if (!(ps2 > 0.0) || !(ps2 < 1.0e300)) return false;  // zero solution, NaN or Inf
+    const double ips = k2f::fast_rsqrt(ps2), ps = ps2 * ips;
+    if (!(ps >= min_norm)) return false;                 // :1752
+    nx = x[0] * ips; ny = x[1] * ips; nz = x[2] * ips; d = ips;
     double worst = 0.0;
 #pragma unroll
     for (int j = 0; j < 5; ++j) {

@@ -184,7 +184,7 @@ struct Iter2Smem {
     double4 plane[kBlock];
     signed char fitres[kBlock];
     int listS[kBlock], listF[kBlock];
-    int nS, nF, qhead;                          // list lengths; head of the tile's work queue (fit batches, then searches)
+    int nS, nF;
 };
 
 // Grid = (blocks per trial, trials).  A trial is one registration (one initial pose) of the context's source against
@@ -256,16 +256,109 @@ __global__ void __launch_bounds__(kBlock, 3) icp_iter2_kernel(const __grid_const
         for (long long base = (long long)blockIdx.x * kBlock; base < A.n; base += (long long)gridDim.x * kBlock) {
             const long long i = base + tid;
             const bool valid = i < A.n;
-            if (tid == 0) { sm.nS = 0; sm.nF = 0; sm.qhead = 0; }
+            if (tid == 0) { sm.nS = 0; sm.nF = 0; }
             __syncthreads();
+            // -- 1. query, previous seven, certificate
             double px = 0.0, py = 0.0, pz = 0.0;
+            bool need = false;
+            if (valid) {
+                const float4 p4 = __ldg(&A.src[i]);
+                px = (double)p4.x; py = (double)p4.y; pz = (double)p4.z;
+                // q = fl32(R p + t)  (utils.hpp:630-636)
+                const float qx = (float)(P.R[0] * px + P.R[1] * py + P.R[2] * pz + P.t[0]);
+                const float qy = (float)(P.R[3] * px + P.R[4] * py + P.R[5] * pz + P.t[1]);
+                const float qz = (float)(P.R[6] * px + P.R[7] * py + P.R[8] * pz + P.t[2]);
+                float B = a.r2_up;
+                need = true;
+                if (use_seeds) {
+                    const int4 s0 = rec_nn[kNnRec * i], s1 = rec_nn[kNnRec * i + 1], s2 = rec_nn[kNnRec * i + 2];   // one round trip
+                    if (s1.z >= 0) {                                          // all seven seeds exist
+                        corr::KnnM nn;
+                        nn.pos[0] = s0.x; nn.pos[1] = s0.y; nn.pos[2] = s0.z; nn.pos[3] = s0.w;
+                        nn.pos[4] = s1.x; nn.pos[5] = s1.y; nn.pos[6] = s1.z;
+#pragma unroll
+                        for (int k = 0; k < corr::kSeeds; ++k) {
+                            const float4 t = __ldg(&g.pts[nn.pos[k]]);
+                            nn.d2[k] = corr::dist2(qx, qy, qz, t);
+                            nn.idx[k] = __float_as_int(t.w);
+                        }
+                        // 16-exchange sorting network on (d2, index)
+#define DCREG_CS(x, y) cswap5(nn.d2[x], nn.idx[x], nn.pos[x], nn.d2[y], nn.idx[y], nn.pos[y])
+                        DCREG_CS(0, 6); DCREG_CS(2, 3); DCREG_CS(4, 5); DCREG_CS(0, 2); DCREG_CS(1, 4); DCREG_CS(3, 6);
+                        DCREG_CS(0, 1); DCREG_CS(2, 5); DCREG_CS(3, 4); DCREG_CS(1, 2); DCREG_CS(4, 6); DCREG_CS(2, 3);
+                        DCREG_CS(4, 5); DCREG_CS(1, 2); DCREG_CS(3, 4); DCREG_CS(5, 6);
+#undef DCREG_CS
+                        B = fminf(B, nn.d2[6] * a.look);
+                        const float ex = qx - __int_as_float(s2.x), ey = qy - __int_as_float(s2.y), ez = qz - __int_as_float(s2.z);
+                        const float delta = sqrtf(ex * ex + ey * ey + ez * ez);
+                        const float lb = __int_as_float(s1.w);
+                        // nothing outside the seven was closer than sqrt(lb) to q_scan; it is now at least sqrt(lb) - delta away
+                        need = !((sqrtf(nn.d2[4]) + delta) * 1.00002f + 1e-7f < sqrtf(lb) * 0.99998f);
+                        if (!need) {
+#pragma unroll
+                            for (int k = 0; k < corr::kSeeds; ++k) sm.res[tid][k] = nn.pos[k];
+                            sm.res[tid][7] = s1.w; sm.res[tid][8] = __float_as_int(nn.d2[4]); sm.res[tid][9] = 1;
+                        }
+                    }
+                }
+                sm.q[tid] = make_float4(qx, qy, qz, B);
+                if (need) { sm.res[tid][9] = 2; ++n_search; }
+            }
+            {   // search list of the tile (slot order)
+                const unsigned bits = __ballot_sync(0xffffffffu, need);
+                int wbase = 0;
+                if (lane == 0 && bits) wbase = atomicAdd(&sm.nS, __popc(bits));
+                wbase = __shfl_sync(0xffffffffu, wbase, 0);
+                if (need) sm.listS[wbase + __popc(bits & ((1u << lane) - 1u))] = tid;
+            }
+            DCREG_STAMP(1);
+            __syncthreads();
+            // -- 2. searches: few -> one warp per listed slot (the other slots' threads are not held up by a
+            //       15 us sequential search); many -> every thread searches for its own slot
+            const int nS = sm.nS;
+            if (coherent && nS <= a.coop_max) {
+                corr::WarpKnnSmem& W = *reinterpret_cast<corr::WarpKnnSmem*>(sm.tbuf[warp]);
+                for (int w = warp; w < nS; w += kBlock / 32) {
+                    const int t = sm.listS[w];
+                    const float4 q = sm.q[t];
+                    corr::KnnM r;
+                    float lbq = a.r2_up * 0.9999f;    // nothing beyond the rings of cells is closer than the radius
+                    const bool got = corr::knn_warp_search(g, q.x, q.y, q.z, q.w, W, r, lbq);
+                    if (got) {
+                        if (lane < corr::kSeeds) sm.res[t][lane] = W.opos[lane];
+                        if (lane == 7) sm.res[t][7] = __float_as_int(lbq);
+                        if (lane == 8) sm.res[t][8] = __float_as_int(r.d2[4]);
+                        if (lane == 9) sm.res[t][9] = 0;
+                    }
+                    __syncwarp();
+                }
+                __syncthreads();
+            }
+            DCREG_STAMP(2);
+            if (valid && sm.res[tid][9] == 2) {       // too many for the list, or more than 64 candidates inside the bound
+                const float4 q = sm.q[tid];
+                if (coherent) {
+                    corr::KnnM r;
+                    float lbq = a.r2_up * 0.9999f;
+                    corr::knn_search_lb(g, q.x, q.y, q.z, q.w, r, lbq);
+#pragma unroll
+                    for (int k = 0; k < corr::kSeeds; ++k) sm.res[tid][k] = r.pos[k];
+                    sm.res[tid][7] = __float_as_int(lbq); sm.res[tid][8] = __float_as_int(r.d2[4]);
+                } else {                              // lean: plain exact 5-NN, nothing kept for the next iteration
+                    corr::Knn5 r;
+                    corr::knn_init(r);
+                    corr::knn_search(g, q.x, q.y, q.z, r);
+#pragma unroll
+                    for (int k = 0; k < 5; ++k) sm.res[tid][k] = r.pos[k];
+                    sm.res[tid][5] = -1; sm.res[tid][6] = -1; sm.res[tid][7] = 0; sm.res[tid][8] = __float_as_int(r.d2[4]);
+                }
+                sm.res[tid][9] = 0;
+            }
+            // -- 3a. record; which five; cached plane?
             double nx = 0.0, ny = 0.0, nz = 0.0, d = 0.0;
-            bool ok = false, want_fit = false, have5 = false, need = false, listed = false;
+            bool ok = false, want_fit = false, have5 = false;
             float d5 = 0.0f;
-            // -- 3a (as a lambda: it runs right after the certificate for a slot that needs no search, after the search
-            //    otherwise).  Record; which five; cached plane?  Input: sm.res[tid] = {pos0..pos6, bits(lb), bits(d2 of the
-            //    5th), 1 = not searched / 0 = searched}.
-            auto decide = [&]() {
+            if (valid) {
                 int pos[corr::kSeeds];
 #pragma unroll
                 for (int k = 0; k < corr::kSeeds; ++k) pos[k] = sm.res[tid][k];
@@ -305,9 +398,19 @@ __global__ void __launch_bounds__(kBlock, 3) icp_iter2_kernel(const __grid_const
                     }
                 }
                 if (!want_fit) { if (coherent) rec_fit[i] = (signed char)fit; ok = fit == 2; }
-            };
-            // one plane fit of the tile's fit list (entry f): by whichever thread picks it up
-            auto do_fit = [&](int f) {
+            }
+            {   // fit list of the tile
+                const unsigned bits = __ballot_sync(0xffffffffu, want_fit);
+                int wbase = 0;
+                if (lane == 0 && bits) wbase = atomicAdd(&sm.nF, __popc(bits));
+                wbase = __shfl_sync(0xffffffffu, wbase, 0);
+                if (want_fit) sm.listF[wbase + __popc(bits & ((1u << lane) - 1u))] = tid;
+            }
+            DCREG_STAMP(3);
+            __syncthreads();
+            // -- 3b. fits, densely packed into the first warps
+            const int nF = sm.nF;
+            for (int f = tid; f < nF; f += kBlock) {
                 const int t = sm.listF[f];
                 int key[5];
 #pragma unroll
@@ -325,129 +428,7 @@ __global__ void __launch_bounds__(kBlock, 3) icp_iter2_kernel(const __grid_const
                     rec_fit[it] = (signed char)fit;
                 }
                 ++n_fit;
-            };
-            auto append_fit = [&]() {     // fit list of the tile (all 32 lanes call this)
-                const unsigned bits = __ballot_sync(0xffffffffu, want_fit && !listed);
-                int wbase = 0;
-                if (lane == 0 && bits) wbase = atomicAdd(&sm.nF, __popc(bits));
-                wbase = __shfl_sync(0xffffffffu, wbase, 0);
-                if (want_fit && !listed) { sm.listF[wbase + __popc(bits & ((1u << lane) - 1u))] = tid; listed = true; }
-            };
-            // -- 1. query, previous seven, certificate
-            if (valid) {
-                const float4 p4 = __ldg(&A.src[i]);
-                int4 s0 = make_int4(-1, -1, -1, -1), s1 = s0, s2 = s0;
-                if (use_seeds) { s0 = rec_nn[kNnRec * i]; s1 = rec_nn[kNnRec * i + 1]; s2 = rec_nn[kNnRec * i + 2]; }   // one round trip
-                px = (double)p4.x; py = (double)p4.y; pz = (double)p4.z;
-                // q = fl32(R p + t)  (utils.hpp:630-636)
-                const float qx = (float)(P.R[0] * px + P.R[1] * py + P.R[2] * pz + P.t[0]);
-                const float qy = (float)(P.R[3] * px + P.R[4] * py + P.R[5] * pz + P.t[1]);
-                const float qz = (float)(P.R[6] * px + P.R[7] * py + P.R[8] * pz + P.t[2]);
-                float B = a.r2_up;
-                need = true;
-                if (use_seeds && s1.z >= 0) {                                 // all seven seeds exist
-                    corr::KnnM nn;
-                    nn.pos[0] = s0.x; nn.pos[1] = s0.y; nn.pos[2] = s0.z; nn.pos[3] = s0.w;
-                    nn.pos[4] = s1.x; nn.pos[5] = s1.y; nn.pos[6] = s1.z;
-#pragma unroll
-                    for (int k = 0; k < corr::kSeeds; ++k) {
-                        const float4 t = __ldg(&g.pts[nn.pos[k]]);
-                        nn.d2[k] = corr::dist2(qx, qy, qz, t);
-                        nn.idx[k] = __float_as_int(t.w);
-                    }
-                    // 16-exchange sorting network on (d2, index)
-#define DCREG_CS(x, y) cswap5(nn.d2[x], nn.idx[x], nn.pos[x], nn.d2[y], nn.idx[y], nn.pos[y])
-                    DCREG_CS(0, 6); DCREG_CS(2, 3); DCREG_CS(4, 5); DCREG_CS(0, 2); DCREG_CS(1, 4); DCREG_CS(3, 6);
-                    DCREG_CS(0, 1); DCREG_CS(2, 5); DCREG_CS(3, 4); DCREG_CS(1, 2); DCREG_CS(4, 6); DCREG_CS(2, 3);
-                    DCREG_CS(4, 5); DCREG_CS(1, 2); DCREG_CS(3, 4); DCREG_CS(5, 6);
-#undef DCREG_CS
-                    B = fminf(B, nn.d2[6] * a.look);
-                    const float ex = qx - __int_as_float(s2.x), ey = qy - __int_as_float(s2.y), ez = qz - __int_as_float(s2.z);
-                    const float delta = sqrtf(ex * ex + ey * ey + ez * ez);
-                    const float lb = __int_as_float(s1.w);
-                    // nothing outside the seven was closer than sqrt(lb) to q_scan; it is now at least sqrt(lb) - delta away
-                    need = !((sqrtf(nn.d2[4]) + delta) * 1.00002f + 1e-7f < sqrtf(lb) * 0.99998f);
-                    if (!need) {
-#pragma unroll
-                        for (int k = 0; k < corr::kSeeds; ++k) sm.res[tid][k] = nn.pos[k];
-                        sm.res[tid][7] = s1.w; sm.res[tid][8] = __float_as_int(nn.d2[4]); sm.res[tid][9] = 1;
-                    }
-                }
-                sm.q[tid] = make_float4(qx, qy, qz, B);
-                if (need) { sm.res[tid][9] = 2; ++n_search; }
-                else decide();                        // no search: its plane fit (if any) can run beside the tile's searches
             }
-            {   // search list of the tile (slot order)
-                const unsigned bits = __ballot_sync(0xffffffffu, need);
-                int wbase = 0;
-                if (lane == 0 && bits) wbase = atomicAdd(&sm.nS, __popc(bits));
-                wbase = __shfl_sync(0xffffffffu, wbase, 0);
-                if (need) sm.listS[wbase + __popc(bits & ((1u << lane) - 1u))] = tid;
-            }
-            append_fit();
-            DCREG_STAMP(1);
-            __syncthreads();
-            // -- 2. one work queue for the tile's warps: batches of 32 plane fits (slots that needed no search) first, then
-            //       the searches, one warp per listed slot (the other slots' threads are not held up by a sequential
-            //       search).  Too many searches -> every thread searches for its own slot instead.
-            const int nS = sm.nS;
-            int fdone = 0;
-            if (coherent && nS <= a.coop_max) {
-                const int nFA = sm.nF, nFb = (nFA + 31) >> 5;
-                corr::WarpKnnSmem& W = *reinterpret_cast<corr::WarpKnnSmem*>(sm.tbuf[warp]);
-                while (true) {
-                    int item = 0;
-                    if (lane == 0) item = atomicAdd(&sm.qhead, 1);
-                    item = __shfl_sync(0xffffffffu, item, 0);
-                    if (item >= nFb + nS) break;
-                    if (item < nFb) {
-                        const int f = item * 32 + lane;
-                        if (f < nFA) do_fit(f);
-                    } else {
-                        const int t = sm.listS[item - nFb];
-                        const float4 q = sm.q[t];
-                        corr::KnnM r;
-                        float lbq = a.r2_up * 0.9999f;    // nothing beyond the rings of cells is closer than the radius
-                        const bool got = corr::knn_warp_search(g, q.x, q.y, q.z, q.w, W, r, lbq);
-                        if (got) {
-                            if (lane < corr::kSeeds) sm.res[t][lane] = W.opos[lane];
-                            if (lane == 7) sm.res[t][7] = __float_as_int(lbq);
-                            if (lane == 8) sm.res[t][8] = __float_as_int(r.d2[4]);
-                            if (lane == 9) sm.res[t][9] = 0;
-                        }
-                    }
-                    __syncwarp();
-                }
-                fdone = nFA;
-                __syncthreads();
-            }
-            DCREG_STAMP(2);
-            if (valid && sm.res[tid][9] == 2) {       // too many for the list, or more than 64 candidates inside the bound
-                const float4 q = sm.q[tid];
-                if (coherent) {
-                    corr::KnnM r;
-                    float lbq = a.r2_up * 0.9999f;
-                    corr::knn_search_lb(g, q.x, q.y, q.z, q.w, r, lbq);
-#pragma unroll
-                    for (int k = 0; k < corr::kSeeds; ++k) sm.res[tid][k] = r.pos[k];
-                    sm.res[tid][7] = __float_as_int(lbq); sm.res[tid][8] = __float_as_int(r.d2[4]);
-                } else {                              // lean: plain exact 5-NN, nothing kept for the next iteration
-                    corr::Knn5 r;
-                    corr::knn_init(r);
-                    corr::knn_search(g, q.x, q.y, q.z, r);
-#pragma unroll
-                    for (int k = 0; k < 5; ++k) sm.res[tid][k] = r.pos[k];
-                    sm.res[tid][5] = -1; sm.res[tid][6] = -1; sm.res[tid][7] = 0; sm.res[tid][8] = __float_as_int(r.d2[4]);
-                }
-                sm.res[tid][9] = 0;
-            }
-            if (valid && need) decide();              // the slots that searched
-            append_fit();
-            DCREG_STAMP(3);
-            __syncthreads();
-            // -- 3b. the remaining fits, densely packed into the first warps
-            const int nF = sm.nF;
-            for (int f = fdone + tid; f < nF; f += kBlock) do_fit(f);
             __syncthreads();
             DCREG_STAMP(4);
             // -- 3c. gate, row, Gram
@@ -1773,11 +1754,10 @@ static int run_loop(dcreg_ctx* ctx, const dcreg_icp_params* params, int trials, 
         if ((rc = enqueue_iterations(ctx, L, params, dlog, dlog ? log_cap : 0, bodies))) return rc;
         issued += bodies;
         if (issued < params->max_iterations && !params->fixed_iterations) {
-            unsigned int* flag = (unsigned int*)ctx->h_pinned;
-            if (L.fold_k2) CK(cudaMemcpyAsync(flag, ctx->d_n_active, sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
-            else CK(cudaMemcpyAsync(flag, &ctx->d_state->done, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+            unsigned int* flag = (unsigned int*)ctx->h_pinned;       // trials still running (every solve step that finishes one decrements it)
+            CK(cudaMemcpyAsync(flag, ctx->d_n_active, sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
             CK(cudaStreamSynchronize(ctx->stream));
-            if (L.fold_k2 ? (*flag == 0u) : (*flag != 0u)) break;
+            if (*flag == 0u) break;
         }
     }
     if (dlog) {
