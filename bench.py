@@ -332,6 +332,7 @@ def run_reference(args, rank, world):
 def run_ours(args, rank, local_rank, world):
     import torch
     import torch.distributed as dist
+    torch.set_num_threads(1)
     from dcreg_b200 import Context, default_params
     from dcreg_b200.scenes import make_cylinder, make_corridor, g2_initial_pose
 
@@ -605,6 +606,11 @@ def main():
         pin_openmp_env(host_cpu_budget()[0])   # before anything loads libgomp: see pin_openmp_env
         run_reference(args, rank, world)
     else:
+        # the GPU arm needs no host parallelism: keep torch's libgomp from parking one spinning thread per visible CPU
+        # (128 of them against a 16-CPU cgroup quota get the launching thread throttled for milliseconds at a time)
+        host_cpu_budget()
+        os.environ["OMP_NUM_THREADS"] = "1"
+        os.environ["OMP_WAIT_POLICY"] = "passive"
         run_ours(args, rank, local_rank, world)
 
 

@@ -642,7 +642,7 @@ __device__ inline void icp_step_warp_ours(const double* acc, IcpState* st, const
         degenerate = __ballot_sync(0xffffffffu, deg) != 0u;
         if (lane < 6) {
             const double* l = sm.lam[lane / 3];
-            sm.ilam[lane / 3][lane % 3] = 1.0 / fmax(l[lane % 3], l[2] / prm.kappa_target);
+            sm.ilam[lane / 3][lane % 3] = k2f::fast_rcp(fmax(l[lane % 3], l[2] * k2f::fast_rcp(prm.kappa_target)));
         }
         __syncwarp();
         for (int e = lane; e < 36; e += 32) {
@@ -674,10 +674,12 @@ __device__ inline void icp_step_warp_ours(const double* acc, IcpState* st, const
     K2_STAMP(4);
     const double dxi = lane < 6 ? sm.dx[lane] : 0.0;
     const bool finite = __ballot_sync(0xffffffffu, !isfinite(dxi)) == 0u;
-    const double fitness = st->n_source_total > 0 ? (double)n_pt / (double)st->n_source_total : 0.0;
-    const double rmse = sqrt(acc[kAccSumR2] / (double)n_eff);
-    if (rec) {
-        if (lane == 0) { rec->rmse = rmse; rec->fitness = fitness; rec->objective = 0.5 * acc[kAccSumB2]; }
+    if (rec) {                                               // log only: off the pose's dependent chain
+        if (lane == 0) {
+            rec->rmse = sqrt(acc[kAccSumR2] / (double)n_eff);
+            rec->fitness = st->n_source_total > 0 ? (double)n_pt / (double)st->n_source_total : 0.0;
+            rec->objective = 0.5 * acc[kAccSumB2];
+        }
         if (lane < 6) rec->gradient[lane] = -acc[21 + lane];
     }
     if (!finite) {                                          // icp_test_runner.cpp:1942-1950
@@ -696,19 +698,54 @@ __device__ inline void icp_step_warp_ours(const double* acc, IcpState* st, const
         return;
     }
     for (int e = lane; e < 36; e += 32) st->H_last[e] = sm.H[e];     // matAtA_last, icp_test_runner.cpp:1965
-    if (lane == 0) {
-        boxplus(sm.Rt, sm.Rt + 9, sm.dx);                    // icp_test_runner.cpp:1953
-        note_step(st, sm.dx, lever, max_step);
-        const double dR = sqrt(sm.dx[0] * sm.dx[0] + sm.dx[1] * sm.dx[1] + sm.dx[2] * sm.dx[2]);
-        const double dT = sqrt(sm.dx[3] * sm.dx[3] + sm.dx[4] * sm.dx[4] + sm.dx[5] * sm.dx[5]);
-        st->iter = iter + 1;
-        if (!prm.fixed_iterations && dR < prm.conv_thresh_rot && dT < prm.conv_thresh_trans) {
-            st->converged = 1; st->done = 1;                 // icp_test_runner.cpp:1998-2002
-        } else if (st->iter >= prm.max_iterations) {
-            st->done = 1;
+    // ---- boxplus (math_utils.hpp:158-166, 20-33), spread over the lanes: R <- R exp(w), t <- t + R_old v.
+    // exp(w) = c I + (1 - c) a a^T + s [a]x with a = w / theta (the same matrix as I + s K + (1 - c) K^2); lane 0 owns
+    // the only long chain (theta, sincos), lanes 0..8 one entry of R exp(w) each, lanes 9..11 one entry of t.
+    {
+        const double wx = sm.dx[0], wy = sm.dx[1], wz = sm.dx[2];
+        const double th2 = wx * wx + wy * wy + wz * wz;
+        const double v2 = sm.dx[3] * sm.dx[3] + sm.dx[4] * sm.dx[4] + sm.dx[5] * sm.dx[5];
+        const double theta = sqrt(th2), dT = sqrt(v2);       // every lane (same instructions, no exchange needed)
+        double e_[9];                                        // exp(w), row-major
+        if (theta < 1e-10) {
+            e_[0] = 1.0; e_[1] = -wz; e_[2] = wy;
+            e_[3] = wz;  e_[4] = 1.0; e_[5] = -wx;
+            e_[6] = -wy; e_[7] = wx;  e_[8] = 1.0;
+        } else {
+            const double ax = wx / theta, ay = wy / theta, az = wz / theta;
+            double sn, cs;
+            sincos(theta, &sn, &cs);
+            const double c1 = 1.0 - cs;
+            // K = [a]x, K^2 = a a^T - I (|a| = 1): I + s K + c1 K^2, written entry by entry as the reference's formula
+            const double K[9] = {0.0, -az, ay, az, 0.0, -ax, -ay, ax, 0.0};
+            const double K2[9] = {-(ay * ay + az * az), ax * ay, ax * az, ax * ay, -(ax * ax + az * az), ay * az,
+                                  ax * az, ay * az, -(ax * ax + ay * ay)};
+#pragma unroll
+            for (int i = 0; i < 9; ++i) e_[i] = ((i % 4 == 0) ? 1.0 : 0.0) + sn * K[i] + c1 * K2[i];
         }
-        const double ms = stamp_iteration(st);               // icp_test_runner.cpp:1973
-        if (rec) rec->iter_time_ms = ms;
+        double outv = 0.0;
+        if (lane < 9) {
+            const int r = lane / 3, c = lane % 3;
+            outv = sm.Rt[r * 3 + 0] * e_[0 * 3 + c] + sm.Rt[r * 3 + 1] * e_[1 * 3 + c] + sm.Rt[r * 3 + 2] * e_[2 * 3 + c];
+        } else if (lane < 12) {
+            const int r = lane - 9;
+            outv = sm.Rt[9 + r] + (sm.Rt[r * 3 + 0] * sm.dx[3] + sm.Rt[r * 3 + 1] * sm.dx[4] + sm.Rt[r * 3 + 2] * sm.dx[5]);
+        }
+        __syncwarp();
+        if (lane < 12) sm.Rt[lane] = outv;
+        if (lane == 0) {
+            st->step_rot = theta; st->step_trans = dT;
+            st->seeds = st->coherent;                        // records exist iff the iteration just done was coherent
+            st->coherent = (theta * lever + dT) < max_step ? 1 : 0;   // largest displacement of any source point (note_step)
+            st->iter = iter + 1;
+            if (!prm.fixed_iterations && theta < prm.conv_thresh_rot && dT < prm.conv_thresh_trans) {
+                st->converged = 1; st->done = 1;             // icp_test_runner.cpp:1998-2002
+            } else if (iter + 1 >= prm.max_iterations) {
+                st->done = 1;
+            }
+            const double ms = stamp_iteration(st);           // icp_test_runner.cpp:1973
+            if (rec) rec->iter_time_ms = ms;
+        }
     }
     __syncwarp();
     K2_STAMP(5);

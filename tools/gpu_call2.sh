@@ -7,7 +7,7 @@ timeout 300 python tools/timeline.py > gpurun_out/timeline.log 2>&1; cat gpurun_
 for v in default NO_GRAPH; do
   if [ $v = default ]; then VARIANT=$v timeout 200 python tools/loop_variants.py; else env VARIANT=$v DCREG_$v=1 timeout 200 python tools/loop_variants.py; fi
 done > gpurun_out/variants.log 2>&1
-cat gpurun_out/variants.log | cut -c1-400
+cat gpurun_out/variants.log | cut -c1-700
 timeout 300 python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/ref_a.json 2> gpurun_out/ref_a.err; echo "ref rc=$?"
 timeout 600 python bench.py --steps 20 --warmup 3 > gpurun_out/bench_a.json 2> gpurun_out/bench_a.err; echo "bench rc=$?"
 tail -c 600 gpurun_out/bench_a.err

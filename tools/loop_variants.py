@@ -31,3 +31,17 @@ with Context(0) as ctx:
     res = ctx.icp_run(prm, T0, want_log=True)
     t = np.array([L.iter_time_ms for L in res.logs]) * 1e3
     print("  iter_time_us:", " ".join(f"{x:.0f}" for x in t), f"| sum {t.sum():.0f}")
+    if os.environ.get("VARIANT", "default") == "default":
+        ctx.iteration_counters(True)
+        prev = (0, 0)
+        rows = []
+        for k in range(1, 51):
+            ctx.icp_run(default_params(search_radius=1.0, max_iterations=k, fixed_iterations=1, kappa_target=10.0), T0, want_log=False)
+            s_, f_ = ctx.iteration_counters(True)
+            rows.append((s_ - prev[0], f_ - prev[1]))
+            prev = (s_, f_)
+        ctx.iteration_counters(False)
+        print("  searched per iteration:", " ".join(str(r[0]) for r in rows))
+        print("  refitted per iteration:", " ".join(str(r[1]) for r in rows))
+        dx = [max(abs(x) for x in L.dx[3:]) for L in res.logs]
+        print("  max |dx_t| per iteration (m):", " ".join(f"{x:.1e}" for x in dx))
