@@ -370,17 +370,20 @@ def run_ours(args, rank, local_rank, world):
     assert res.iterations == C2_ITERS
 
     sampler = ClockSampler(local_rank)
-    barrier()
     if rank == 0:
         sampler.start()
+        time.sleep(0.3)                                   # let nvidia-smi finish starting up before anything is timed
+    barrier()
     l0 = ctx.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record(stream)
     for _ in range(args.steps):
-        res = ctx.icp_run(prm, T0, want_log=False)       # inputs resident in HBM
-    e1.record(stream)
+        ctx.icp_enqueue(prm, T0)                         # inputs resident in HBM; the device never waits for the host:
+    e1.record(stream)                                    # the K runs are queued back to back (dcreg_icp_enqueue)
     e1.synchronize()
+    res = ctx.icp_fetch()
+    assert res.iterations == C2_ITERS
     barrier()
     dev_ms = max_over_ranks(e0.elapsed_time(e1))
     launches = ctx.launch_count - l0

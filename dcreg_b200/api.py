@@ -87,7 +87,7 @@ EXPORTS = [
     "dcreg_stream", "dcreg_set_source", "dcreg_set_target", "dcreg_find_planes",
     "dcreg_reduce_normal_equations", "dcreg_reduce_normal_equations_f64plane",
     "dcreg_reduce_normal_equations_host", "dcreg_analyze_and_solve", "dcreg_solve_pcg", "dcreg_icp_run",
-    "dcreg_icp_run_batch", "dcreg_icp_run_host_planes", "dcreg_comm_mode", "dcreg_last_covariance", "dcreg_point_to_point_metrics", "dcreg_comm_unique_id", "dcreg_comm_init",
+    "dcreg_icp_run_batch", "dcreg_icp_enqueue", "dcreg_icp_fetch", "dcreg_icp_run_host_planes", "dcreg_comm_mode", "dcreg_last_covariance", "dcreg_point_to_point_metrics", "dcreg_comm_unique_id", "dcreg_comm_init",
     "dcreg_comm_destroy", "dcreg_set_global_source_count", "dcreg_launch_count", "dcreg_device_source",
     "dcreg_device_planes_f64", "dcreg_device_planes_f32", "dcreg_freeze_planes_f32", "dcreg_time_reduce", "dcreg_time_iteration", "dcreg_iteration_counters", "dcreg_iteration_timeline",
 ]
@@ -123,6 +123,8 @@ def load_library():
     lib.dcreg_icp_run_batch.argtypes = [vp, C.POINTER(IcpParams), ci, dp, dp, C.POINTER(ci), C.POINTER(ci), C.POINTER(ci),
                                         C.POINTER(IterLog), ci]
     lib.dcreg_comm_mode.argtypes = [vp]
+    lib.dcreg_icp_enqueue.argtypes = [vp, C.POINTER(IcpParams), dp]
+    lib.dcreg_icp_fetch.argtypes = [vp, dp, C.POINTER(ci), C.POINTER(ci)]
     lib.dcreg_icp_run_host_planes.argtypes = [vp, C.POINTER(IcpParams), dp, PLANE_CALLBACK, vp, dp,
                                               C.POINTER(IterLog), ci, C.POINTER(ci), C.POINTER(ci)]
     lib.dcreg_last_covariance.argtypes = [vp, dp]
@@ -338,6 +340,18 @@ class Context:
         return IcpResult(rc, bool(conv.value), n_it.value, T_out, [logs[i] for i in range(nrec)])
 
     Point2PlaneICP_SO3 = icp_run
+
+    def icp_enqueue(self, params: IcpParams, T_init):
+        """Put a whole run on the context's stream without any host synchronisation (see icp_fetch)."""
+        T_init = np.ascontiguousarray(T_init, dtype=np.float64)
+        self._check(self.lib.dcreg_icp_enqueue(self._h, C.byref(params), _dptr(T_init)))
+
+    def icp_fetch(self) -> IcpResult:
+        """Wait for the stream; pose / iteration count / flags of the last enqueued run."""
+        T_out = np.empty((4, 4)); n_it = C.c_int(0); conv = C.c_int(0)
+        rc = self._check(self.lib.dcreg_icp_fetch(self._h, _dptr(T_out), C.byref(n_it), C.byref(conv)),
+                         allow=(NOT_ENOUGH_POINTS, NONFINITE_UPDATE))
+        return IcpResult(rc, bool(conv.value), n_it.value, T_out, [])
 
     def icp_run_batch(self, params: IcpParams, T_init, want_log: bool = False):
         """`num_runs` registrations side by side (icp_test_runner.cpp:331-345): T_init (B, 4, 4).

@@ -1730,8 +1730,9 @@ static int enqueue_iterations(dcreg_ctx* ctx, LoopPlan& L, const dcreg_icp_param
 }
 
 // The loop for `trials` registrations of the context's source against its target, side by side.
+// fetch = false: enqueue only (no host synchronisation at all: no peek between chunks, no read-back)
 static int run_loop(dcreg_ctx* ctx, const dcreg_icp_params* params, int trials, const double* T_init, double* T_out,
-                    dcreg_iter_log* log, int log_cap, int* n_iterations, int* converged, int* status) {
+                    dcreg_iter_log* log, int log_cap, int* n_iterations, int* converged, int* status, bool fetch = true) {
     int rc;
     if (log && log_cap > 0 && (rc = ensure_log(ctx, (long long)trials * log_cap))) return rc;
     dcreg_iter_log* dlog = (log && log_cap > 0) ? ctx->d_log : nullptr;
@@ -1753,7 +1754,7 @@ static int run_loop(dcreg_ctx* ctx, const dcreg_icp_params* params, int trials, 
         const int bodies = (todo < chunk && issued > 0) ? chunk : todo;
         if ((rc = enqueue_iterations(ctx, L, params, dlog, dlog ? log_cap : 0, bodies))) return rc;
         issued += bodies;
-        if (issued < params->max_iterations && !params->fixed_iterations) {
+        if (fetch && issued < params->max_iterations && !params->fixed_iterations) {
             unsigned int* flag = (unsigned int*)ctx->h_pinned;       // trials still running (every solve step that finishes one decrements it)
             CK(cudaMemcpyAsync(flag, ctx->d_n_active, sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
             CK(cudaStreamSynchronize(ctx->stream));
@@ -1764,6 +1765,7 @@ static int run_loop(dcreg_ctx* ctx, const dcreg_icp_params* params, int trials, 
         log_fill_kernel<<<dim3((log_cap + 31) / 32, trials), 32, 0, ctx->stream>>>(dlog, log_cap, ctx->d_state, *params);
         ctx->launches++;
     }
+    if (!fetch) return DCREG_OK;
     return read_results(ctx, trials, T_out, log, log_cap, n_iterations, converged, status);
 }
 
@@ -1788,6 +1790,24 @@ int dcreg_icp_run(dcreg_ctx* ctx, const dcreg_icp_params* params, const double T
     int status = DCREG_OK;
     if ((rc = run_loop(ctx, params, 1, T_init, T_out, log, log_cap, n_iterations, converged, &status))) return rc;
     return status;
+}
+
+int dcreg_icp_enqueue(dcreg_ctx* ctx, const dcreg_icp_params* params, const double T_init[16]) {
+    if (!ctx) return DCREG_BAD_ARG;
+    if (!params || !T_init) { ctx->err = "icp_enqueue: null pointer"; return DCREG_BAD_ARG; }
+    int rc = check_run_args(ctx, params);
+    if (rc) return rc;
+    CK(cudaSetDevice(ctx->device));
+    return run_loop(ctx, params, 1, T_init, nullptr, nullptr, 0, nullptr, nullptr, nullptr, false);
+}
+
+int dcreg_icp_fetch(dcreg_ctx* ctx, double T_out[16], int* n_iterations, int* converged) {
+    if (!ctx) return DCREG_BAD_ARG;
+    if (!T_out) { ctx->err = "icp_fetch: null pointer"; return DCREG_BAD_ARG; }
+    CK(cudaSetDevice(ctx->device));
+    int status = DCREG_OK;
+    const int rc = read_results(ctx, 1, T_out, nullptr, 0, n_iterations, converged, &status);
+    return rc ? rc : status;
 }
 
 int dcreg_icp_run_batch(dcreg_ctx* ctx, const dcreg_icp_params* params, int n_trials, const double* T_init,

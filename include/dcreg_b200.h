@@ -201,6 +201,12 @@ int dcreg_solve_pcg(dcreg_ctx* ctx, const double A[36], const double b[6], const
 int dcreg_icp_run(dcreg_ctx* ctx, const dcreg_icp_params* params, const double T_init[16],
                   double T_out[16], dcreg_iter_log* log, int log_cap, int* n_iterations,
                   int* converged);
+/* The same run split in two for callers that pipeline scans: dcreg_icp_enqueue puts the whole run (all max_iterations
+ * loop bodies; iterations past convergence exit at once on the device) on the context's stream and returns without any
+ * host synchronisation; dcreg_icp_fetch waits for the stream and returns the pose / iteration count / flags of the LAST
+ * enqueued run with dcreg_icp_run's return value.  No per-iteration log on this path. */
+int dcreg_icp_enqueue(dcreg_ctx* ctx, const dcreg_icp_params* params, const double T_init[16]);
+int dcreg_icp_fetch(dcreg_ctx* ctx, double T_out[16], int* n_iterations, int* converged);
 /* Many registrations of the SAME source against the SAME target from different initial poses, side by side in one
  * sequence of launches (trial = grid y-dimension; each trial owns its loop state, neighbour records and log slice, and
  * stops on its own convergence test).  Replaces the `num_runs` loop of TestRunner::runSingleTest

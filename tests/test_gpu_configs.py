@@ -68,6 +68,11 @@ def test_c2_as_benchmarked_matches_oracle_every_iteration(ctx):
     # a second run on the same context (graph replay, records of the previous run discarded) gives the same bits
     res2 = ctx.icp_run(gp, T0)
     assert np.array_equal(res2.T, res.T)
+    # ... and so do runs queued back to back without any host synchronisation (dcreg_icp_enqueue / dcreg_icp_fetch)
+    ctx.icp_enqueue(gp, T0)
+    ctx.icp_enqueue(gp, T0)
+    res3 = ctx.icp_fetch()
+    assert res3.status == 0 and res3.iterations == 50 and np.array_equal(res3.T, res.T)
     sc.close()
 
 
