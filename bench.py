@@ -395,13 +395,18 @@ def run_ours(args, rank, local_rank, world):
     searched, fitted = ctx.iteration_counters(False)
 
     # e2e: host buffers in, pose + log out, every step
+    ctx.set_source(pts_pinned)
+    res = ctx.icp_run(prm, T0, want_log=True)            # untimed: this run shape's first use (graph capture)
     barrier()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    step_wall = []
     w0 = time.perf_counter()
     e2.record(stream)
     for _ in range(args.steps):
+        ws = time.perf_counter()
         ctx.set_source(pts_pinned)                        # H2D of this step's scan (pinned)
         res = ctx.icp_run(prm, T0, want_log=True)         # D2H of pose + per-iteration records
+        step_wall.append(time.perf_counter() - ws)
     e3.record(stream)
     e3.synchronize()
     wall = time.perf_counter() - w0
@@ -559,7 +564,8 @@ def run_ours(args, rank, local_rank, world):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(world),
             "e2e": {"value": e2e_value, "unit": "ICP iterations/s", "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps},
+                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps,
+                    "step_wall_ms": {"min": 1e3 * min(step_wall), "median": 1e3 * float(np.median(step_wall)), "max": 1e3 * max(step_wall)}},
             "gpu_launches": int(launches),
             "loop": {"slot_iterations_per_step": C2_POINTS * C2_ITERS, "searched": int(searched), "plane_fits": int(fitted),
                      "note": "every iteration recomputes every correspondence; a slot whose 7 stored neighbours provably still "

@@ -746,11 +746,13 @@ __device__ __forceinline__ bool fit_plane(const Grid& g, const int (&kpos)[5], d
     return worst < thickness * thickness;                // :1772-1773
 }
 
-// The same fit with the register-resident QR (small_la.cuh: same operations in the same order, divisions and square roots
-// through the hardware seeds + Newton: a fit is ONE thread's dependent chain, 7 us of every loop iteration with the IEEE
-// sequences).  A separate function with its own register allocation: it is called from the fit work list of the loop
-// kernel, where almost nothing is live across the call (inlined into a loop body full of live state it spills; measured
-// 3.7x slower there).  A cached plane is reused only by the loop kernel itself, so reuse stays bit-identical to a refit.
+// The same fit with the register-resident QR (small_la.cuh: same operations in the same order, bit-identical results).  A
+// separate function with its own register allocation: it is called from the fit work list of the loop kernel, where
+// almost nothing is live across the call (inlined into a loop body full of live state it spills; measured 3.7x slower
+// there).  Measured and rejected (round 2): the kFast variant of the QR (hardware reciprocal / rsqrt seeds instead of the
+// ~30 IEEE divisions and square roots on the fit's dependent chain) makes a fit 7 -> 6 us, but on exactly rank-deficient
+// neighbourhoods (collinear lattice points) its 1-ulp differences flip the pivoted QR's rank decision, and the loop then
+// disagrees with the generic fit by one correspondence (tests/test_gpu_parity.py, lattice scene).
 __device__ __noinline__ bool fit_plane_reg(const Grid& g, const int (&kpos)[5], double min_norm, double thickness,
                                            double& nx, double& ny, double& nz, double& d) {
     double A[5][3], b[5], x[3];
@@ -762,12 +764,10 @@ __device__ __noinline__ bool fit_plane_reg(const Grid& g, const int (&kpos)[5], 
         A[j][2] = (double)p.z;
         b[j] = -1.0;
     }
-    dla::colpiv_qr_solve_reg<5, 3, true>(A, b, x);
-    const double ps2 = x[0] * x[0] + x[1] * x[1] + x[2] * x[2];
-    if (!(ps2 > 0.0) || !(ps2 < 1.0e300)) return false;  // zero solution, NaN or Inf
-    const double ips = k2f::fast_rsqrt(ps2), ps = ps2 * ips;
-    if (!(ps >= min_norm)) return false;                 // :1752
-    nx = x[0] * ips; ny = x[1] * ips; nz = x[2] * ips; d = ips;
+    dla::colpiv_qr_solve_reg<5, 3>(A, b, x);
+    const double ps = sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
+    if (!(ps >= min_norm)) return false;                 // :1752 (also rejects NaN)
+    nx = x[0] / ps; ny = x[1] / ps; nz = x[2] / ps; d = 1.0 / ps;
     double worst = 0.0;
 #pragma unroll
     for (int j = 0; j < 5; ++j) {

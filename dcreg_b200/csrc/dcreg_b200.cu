@@ -733,9 +733,12 @@ struct dcreg_ctx {
     int nn_trials = 0;                    // trials the per-slot record arrays (d_nn, d_plane_cache, ...) are sized for
     dcreg_iter_log* d_log = nullptr; long long log_cap = 0;   // records, [trials][log_cap of the run]
     bool loop_attr_done = false, k1_attr_done[8] = {false, false, false, false, false, false, false, false};
-    // CUDA graph of one chunk of loop iterations (keyed on the kernel arguments)
-    cudaGraphExec_t graph_exec = nullptr; std::vector<unsigned char> graph_key; bool graph_off = false;
+    // CUDA graphs of one chunk of loop iterations, keyed on the kernel arguments (a few shapes alternate in practice:
+    // with / without a log, one trial / a batch); most recently used first
+    struct LoopGraph { std::vector<unsigned char> key; cudaGraphExec_t exec; };
+    std::vector<LoopGraph> graphs; bool graph_off = false;
     long long graph_launches = 0;
+    void drop_graphs() { for (auto& g : graphs) if (g.exec) cudaGraphExecDestroy(g.exec); graphs.clear(); }
     double* d_small = nullptr;       // scratch for the seams (>= 512 doubles)
     K2Scratch* d_k2_scratch = nullptr;   // K2's rehearsal state (see k2_step_kernel)
     dcreg_analysis* d_analysis = nullptr;
@@ -812,7 +815,7 @@ int ensure_trials(dcreg_ctx* ctx, int trials) {
     CK(cudaMemsetAsync(ctx->d_state, 0, (size_t)trials * sizeof(IcpState), ctx->stream));
     CK(cudaMalloc(&ctx->d_T_init, (size_t)trials * 16 * sizeof(double)));
     ctx->trials_cap = trials;
-    if (ctx->graph_exec) { cudaGraphExecDestroy(ctx->graph_exec); ctx->graph_exec = nullptr; ctx->graph_key.clear(); }
+    ctx->drop_graphs();
     return DCREG_OK;
 }
 
@@ -1015,7 +1018,7 @@ int dcreg_destroy(dcreg_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     dcreg_comm_destroy(ctx);
-    if (ctx->graph_exec) cudaGraphExecDestroy(ctx->graph_exec);
+    ctx->drop_graphs();
     void* ptrs[] = {ctx->d_n_active, ctx->d_T_init, ctx->d_sort_tmp, ctx->d_src, ctx->d_stage, ctx->d_tgt, ctx->grid.keys, ctx->grid.cell_start, ctx->grid.hstart,
                     ctx->grid.hcount, ctx->d_src_sorted, ctx->d_cell_tmp, ctx->d_pt_cell, ctx->d_tile_sums,
                     ctx->grid.pts, ctx->d_planes64, ctx->d_planes32, ctx->d_partials, ctx->d_counter, ctx->d_acc,
@@ -1693,9 +1696,14 @@ static int enqueue_iterations(dcreg_ctx* ctx, LoopPlan& L, const dcreg_icp_param
         const int meta[4] = {L.grid_x, L.trials, L.use_wd ? 1 : 0, iters};
         key_bytes(key, meta, sizeof(meta));
         key_bytes(key, prm, sizeof(*prm));
-        if (!ctx->graph_exec || key != ctx->graph_key) {
-            if (ctx->graph_exec) { cudaGraphExecDestroy(ctx->graph_exec); ctx->graph_exec = nullptr; }
-            ctx->graph_key.clear();
+        cudaGraphExec_t exec = nullptr;
+        for (size_t gi = 0; gi < ctx->graphs.size(); ++gi)
+            if (ctx->graphs[gi].key == key) {
+                if (gi != 0) std::swap(ctx->graphs[gi], ctx->graphs[0]);
+                exec = ctx->graphs[0].exec;
+                break;
+            }
+        if (!exec) {
             cudaGraph_t graph = nullptr;
             const bool nn_valid0 = ctx->nn_valid;
             const long long launches0 = ctx->launches;
@@ -1706,17 +1714,18 @@ static int enqueue_iterations(dcreg_ctx* ctx, LoopPlan& L, const dcreg_icp_param
                 e = cudaStreamEndCapture(ctx->stream, &graph);
             }
             ctx->nn_valid = nn_valid0; ctx->launches = launches0;      // nothing has run yet
-            if (e == cudaSuccess && rc == DCREG_OK && graph) e = cudaGraphInstantiate(&ctx->graph_exec, graph, 0);
+            if (e == cudaSuccess && rc == DCREG_OK && graph) e = cudaGraphInstantiate(&exec, graph, 0);
             if (graph) cudaGraphDestroy(graph);
-            if (e != cudaSuccess || rc != DCREG_OK || !ctx->graph_exec) {
+            if (e != cudaSuccess || rc != DCREG_OK || !exec) {
                 cudaGetLastError();                                    // clear; run without a graph from now on
-                ctx->graph_exec = nullptr; ctx->graph_off = true;
+                exec = nullptr; ctx->graph_off = true;
             } else {
-                ctx->graph_key = key;
+                if (ctx->graphs.size() >= 4) { cudaGraphExecDestroy(ctx->graphs.back().exec); ctx->graphs.pop_back(); }
+                ctx->graphs.insert(ctx->graphs.begin(), dcreg_ctx::LoopGraph{key, exec});
             }
         }
-        if (ctx->graph_exec) {
-            CK(cudaGraphLaunch(ctx->graph_exec, ctx->stream));
+        if (exec) {
+            CK(cudaGraphLaunch(exec, ctx->stream));
             ctx->nn_valid = true;
             ctx->launches += (long long)iters * (L.fold_k2 ? 1 : 2); ctx->graph_launches++;
             return DCREG_OK;
@@ -1976,7 +1985,7 @@ int dcreg_comm_init(dcreg_ctx* ctx, const uint8_t nccl_unique_id[128], int rank,
     }
     ctx->rank = rank; ctx->nranks = nranks;
     setup_peer_mailboxes(ctx);
-    if (ctx->graph_exec) { cudaGraphExecDestroy(ctx->graph_exec); ctx->graph_exec = nullptr; ctx->graph_key.clear(); }
+    ctx->drop_graphs();
     return DCREG_OK;
 }
 
@@ -1994,7 +2003,7 @@ int dcreg_comm_destroy(dcreg_ctx* ctx) {
     if (ctx->d_mailbox) { cudaFree(ctx->d_mailbox); ctx->d_mailbox = nullptr; }
     ctx->peer_ok = false; ctx->peer_view = peer::View{};
     ctx->comm = nullptr; ctx->rank = 0; ctx->nranks = 1;
-    if (ctx->graph_exec) { cudaGraphExecDestroy(ctx->graph_exec); ctx->graph_exec = nullptr; ctx->graph_key.clear(); }
+    ctx->drop_graphs();
     return DCREG_OK;
 }
 
