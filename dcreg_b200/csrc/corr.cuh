@@ -295,6 +295,33 @@ __device__ __forceinline__ void knn_search(const Grid& g, float qx, float qy, fl
         // by an absolute eps that covers that rounding, so a bound can only be too small (never prunes a hit)
         const float eps = 2e-6f * (fabsf(qx) + fabsf(qy) + fabsf(qz) + cell);
         const float fx = qx - (float)cx * cell, fy = qy - (float)cy * cell, fz = qz - (float)cz * cell;
+        if (K == 1) {
+            // cell = search radius (the usual set-up): 9 rows of 3 cells.  Same rows, same pruning tests and the same
+            // own / left / right order as the general loop below, but a row's FOUR cell boundaries are fetched together
+            // (one memory round trip per visited row instead of up to six dependent ones: the lanes of a warp prune
+            // differently, so a warp walks nearly all 27 cells and every dependent load is on its critical path).
+            const float gl = fmaxf(fx - eps, 0.0f), gr = fmaxf((cell - fx) - eps, 0.0f);
+            const float gl2 = gl * gl * 0.99999f, gr2 = gr * gr * 0.99999f;
+            const int xa = min(max(lx - 1, 0), g.nx), xb = min(max(lx, 0), g.nx), xc = min(max(lx + 1, 0), g.nx), xd = min(max(lx + 2, 0), g.nx);
+#pragma unroll 1
+            for (int r = 0; r < 9; ++r) {
+                // own row first, then the ring: (dz, dy) = (-1,-1) (-1,0) (-1,1) (0,-1) (0,1) (1,-1) (1,0) (1,1)
+                const int q = r == 0 ? 4 : (r <= 4 ? r - 1 : r);
+                const int dz = q / 3 - 1, dy = q % 3 - 1;
+                const int zz = lz + dz, yy = ly + dy;
+                if (zz < 0 || zz >= g.nz || yy < 0 || yy >= g.ny) continue;
+                const float gz = dz == 0 ? 0.0f : fmaxf((dz < 0 ? fz : cell - fz) - eps, 0.0f);
+                const float gy = dy == 0 ? 0.0f : fmaxf((dy < 0 ? fy : cell - fy) - eps, 0.0f);
+                const float row_lb = (gy * gy + gz * gz) * 0.99999f;
+                if (row_lb > k.d2[4]) continue;
+                const int* rowp = g.cell_start + (size_t)(zz * g.ny + yy) * g.nx;
+                const int b0 = __ldg(rowp + xa), b1 = __ldg(rowp + xb), b2 = __ldg(rowp + xc), b3 = __ldg(rowp + xd);
+                knn_scan_range(g.pts, b1, b2, qx, qy, qz, k);
+                if (row_lb + gl2 <= k.d2[4]) knn_scan_range(g.pts, b0, b1, qx, qy, qz, k);
+                if (row_lb + gr2 <= k.d2[4]) knn_scan_range(g.pts, b2, b3, qx, qy, qz, k);
+            }
+            return;
+        }
 #pragma unroll 1
         for (int ring = 0; ring <= K; ++ring) {
             // a whole ring is at least (ring - 1) * cell + (distance to the own cell's nearest face) away
