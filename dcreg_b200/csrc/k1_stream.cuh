@@ -205,8 +205,7 @@ __device__ __forceinline__ bool reduce_to_fin(double mine, TailSmem& ts, double*
 #pragma unroll
             for (int u = 0; u < kRows; ++u) s += t[u];
         }
-        __syncthreads();                                          // red[][] is free again
-        ts.red[warp][lane] = s;
+        ts.red[warp][lane] = s;                                   // (red[][] was last read before the ticket's barrier)
     }
     __syncthreads();
     if (warp == 0) {
@@ -400,9 +399,11 @@ __global__ void __launch_bounds__(kThreads, 2) reduce_stream_kernel(const __grid
     }
     if (a.debug == 2) { if (v[0] == 1.2345) a.acc[0] = v[0]; return; }
     if (!reduce_to_fin(v[0], sm.tail, a.partials, a.counter, (int)blockIdx.x, (int)gridDim.x)) return;
-    if (a.npt_override >= 0.0 && tid == 0) sm.tail.fin[kPkNpt] = a.npt_override;
-    __syncthreads();
-    peer::all_reduce32(a.peer, sm.tail.fin, sm.tail.red);
+    if (a.peer.nranks > 1 || a.npt_override >= 0.0) {             // (uniform) host-kd-tree count, sum over ranks
+        if (a.npt_override >= 0.0 && tid == 0) sm.tail.fin[kPkNpt] = a.npt_override;
+        __syncthreads();
+        peer::all_reduce32(a.peer, sm.tail.fin, sm.tail.red);
+    }
     congruence(sm.tail.fin, a.pose.R, a.acc);
 }
 
