@@ -2,21 +2,24 @@
 //
 // the path shards by contiguous source-point blocks and has exactly ONE exchange per ICP iteration -
 // the sum over ranks of the 27 + 5 accumulators (the OpenMP `reduction(+: ...)` of icp_test_runner.cpp:1714 and
-// SymmetricHessianComputer::join, hessian_computer.h:103-108).  240 B per rank: pure latency.  A separate
+// SymmetricHessianComputer::join, hessian_computer.h:103-108).  256 B per rank: pure latency.  A separate
 // ncclAllReduce kernel behind the reduction costs ~25 us per iteration (round 1: 65.9 -> 40.5 us for 10 M slots on
 // 8 GPUs, i.e. 1.6x), so the exchange lives in the LAST BLOCK of the reducing kernel instead:
 //
-//   every rank owns a 4.3 KB mailbox in its own HBM, mapped into every peer's address space (cudaIpc handles
+//   every rank owns an 8 KB mailbox in its own HBM, mapped into every peer's address space (cudaIpc handles
 //   exchanged once in dcreg_comm_init; NVLink 5 / NVSwitch P2P stores);
 //   epoch e (same on all ranks: every rank runs the same sequence of reductions):
 //     post : warp q of the last block stores this rank's 32 packed totals into rank q's mailbox slot
-//            data[e & 1][my_rank][0..31], fences (system scope) and releases flag[my_rank] = e there;
-//     wait : warp q spins (acquire, system scope) on ITS OWN mailbox's flag[q] until it reaches e, then reads
-//            data[e & 1][q][lane];
+//            pkt[e & 1][my_rank][0..63] as 64 self-validating 8-byte packets {32 data bits, epoch}: an aligned 8-byte
+//            store is single-copy atomic, so a packet is either old or complete - no fence, no separate flag, one
+//            NVLink store latency (the "LL" idea of collective libraries);
+//     wait : warp q spins on ITS OWN mailbox's pkt[e & 1][q][2 lane], [2 lane + 1] until both carry epoch e and
+//            reassembles the double;
 //     sum  : in rank order 0..N-1 - the same order on every rank, so all ranks hold bit-identical sums and the
 //            solve that follows (K2, redundantly on every rank) yields bit-identical poses: no broadcast needed.
-//   Two data slots (epoch parity) suffice: a rank can only post epoch e + 1 after it has received every peer's
-//   epoch e, and a peer posts epoch e only after it finished reading epoch e - 1.
+//   Two slots (epoch parity) suffice: a rank can only post epoch e + 1 after it has received every peer's epoch e,
+//   and a peer posts epoch e only after it finished reading epoch e - 1 (tests/test_peer_protocol.py runs a model of
+//   this under adversarial interleavings).
 // No rank waits before it has posted, so the exchange cannot deadlock; a peer that never posts (crashed process)
 // trips a 4 s globaltimer timeout, which raises `error` in the mailbox instead of hanging the GPU.
 // NCCL (dcreg_b200.cu: nccl_allreduce_acc) remains as the fallback when peer mapping is unavailable.
@@ -30,8 +33,7 @@ constexpr int kMaxRanks = 8;     // one warp of the 256-thread last block per ra
 constexpr int kVals = 32;        // k1s::kPk packed totals
 
 struct Mailbox {
-    double data[2][kMaxRanks][kVals];
-    unsigned int flag[kMaxRanks];        // written by peer r: epoch of its latest complete contribution
+    unsigned long long pkt[2][kMaxRanks][2 * kVals];   // written by peer r: {low / high half of a double, epoch} packets
     unsigned int epoch;                  // this rank's own epoch counter (local)
     unsigned int error;                  // != 0: a wait timed out
     unsigned int pad[6];
@@ -43,20 +45,12 @@ struct View {
     Mailbox* box[kMaxRanks];             // box[r]: rank r's mailbox in THIS process's address space (box[rank] is local)
 };
 
-__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+__device__ __forceinline__ void st_relaxed_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
-__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
-    unsigned int v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_relaxed_sys(double* p, double v) {
-    asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
-}
-__device__ __forceinline__ double ld_relaxed_sys(const double* p) {
-    double v;
-    asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+__device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
 
@@ -68,27 +62,28 @@ __device__ __forceinline__ void all_reduce32(const View& pv, double* fin, double
     Mailbox* mine = pv.box[pv.rank];
     const unsigned int e = mine->epoch + 1u;            // read by everyone before thread 0 advances it below
     const double v = fin[lane];
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
+    const unsigned long long tag = (unsigned long long)e << 32;
     for (int q = warp; q < pv.nranks; q += nwarps) {    // post
         if (q == pv.rank) { red[q][lane] = v; continue; }
-        Mailbox* dst = pv.box[q];
-        st_relaxed_sys(&dst->data[e & 1u][pv.rank][lane], v);
-        __threadfence_system();
-        __syncwarp();
-        if (lane == 0) st_release_sys(&dst->flag[pv.rank], e);
+        unsigned long long* dst = pv.box[q]->pkt[e & 1u][pv.rank];
+        st_relaxed_sys(dst + 2 * lane, (bits & 0xffffffffull) | tag);
+        st_relaxed_sys(dst + 2 * lane + 1, (bits >> 32) | tag);
     }
     for (int q = warp; q < pv.nranks; q += nwarps) {    // wait
         if (q == pv.rank) continue;
-        if (lane == 0) {
-            unsigned long long t0 = 0;
-            while ((int)(ld_acquire_sys(&mine->flag[q]) - e) < 0) {
-                unsigned long long now;
-                asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
-                if (t0 == 0) t0 = now;
-                else if (now - t0 > 4000000000ull) { mine->error = 1u + (unsigned)q; break; }
-            }
+        const unsigned long long* src = mine->pkt[e & 1u][q];
+        unsigned long long p0, p1, t0 = 0;
+        while (true) {
+            p0 = ld_relaxed_sys(src + 2 * lane);
+            p1 = ld_relaxed_sys(src + 2 * lane + 1);
+            if ((unsigned int)(p0 >> 32) == e && (unsigned int)(p1 >> 32) == e) break;
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 4000000000ull) { mine->error = 1u + (unsigned)q; p0 = p1 = 0; break; }
         }
-        __syncwarp();
-        red[q][lane] = ld_relaxed_sys(&mine->data[e & 1u][q][lane]);
+        red[q][lane] = __longlong_as_double((long long)((p0 & 0xffffffffull) | (p1 << 32)));
     }
     __syncthreads();
     if (tid < kVals) {

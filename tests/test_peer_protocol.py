@@ -3,8 +3,8 @@
 The device code cannot run here (no GPU), so - like tests/test_certificate_logic.py does for the gap certificate - the
 protocol is restated step by step and a random scheduler interleaves the ranks' atomic steps:
 
-  epoch e on rank r:  for every peer q: write data[q][e & 1][r], then release flag[q][r] = e
-                      for every peer q: spin until flag[r][q] >= e, then read data[r][e & 1][q]
+  epoch e on rank r:  for every peer q: store the packet {value, epoch e} into pkt[q][e & 1][r]   (one atomic 8-byte store)
+                      for every peer q: spin until pkt[r][e & 1][q] carries epoch e, then take its value
                       sum in rank order
 
 Checked: no rank ever reads a slot that a faster peer has already overwritten with a later epoch (the two-slot parity
@@ -23,7 +23,6 @@ class Rank:
         self.e = 1
         self.phase = "post"
         self.todo = [q for q in range(n) if q != r]
-        self.pending_flag = None
         self.got = {}
         self.sums = []
         self.corrupt = False
@@ -35,8 +34,7 @@ class Rank:
 def run(n, epochs, slots, seed, greedy_rank=None):
     rng = random.Random(seed)
     vals = np.random.default_rng(seed).standard_normal((epochs + 1, n))
-    data = [[[None] * n for _ in range(slots)] for _ in range(n)]      # data[owner][slot][src] = (epoch, value)
-    flag = [[0] * n for _ in range(n)]                                  # flag[owner][src]
+    data = [[[(0, 0.0)] * n for _ in range(slots)] for _ in range(n)]  # pkt[owner][slot][src] = (epoch, value)
     ranks = [Rank(r, n, epochs, vals) for r in range(n)]
     steps = 0
     while not all(k.done() for k in ranks):
@@ -48,21 +46,17 @@ def run(n, epochs, slots, seed, greedy_rank=None):
             k = ranks[greedy_rank]                                       # one rank runs far ahead whenever it can
         e = k.e
         if k.phase == "post":
-            if k.pending_flag is not None:                               # release store after the data store
-                flag[k.pending_flag][k.r] = e
-                k.pending_flag = None
-                if not k.todo:
-                    k.phase, k.todo = "wait", [q for q in range(n) if q != k.r]
-            else:
-                q = k.todo.pop()
-                data[q][e % slots][k.r] = (e, float(vals[e, k.r]))
-                k.pending_flag = q
+            q = k.todo.pop()
+            data[q][e % slots][k.r] = (e, float(vals[e, k.r]))           # self-validating packet
+            if not k.todo:
+                k.phase, k.todo = "wait", [q2 for q2 in range(n) if q2 != k.r]
         else:
             q = k.todo[-1]
-            if flag[k.r][q] >= e:                                        # acquire
-                ep, v = data[k.r][e % slots][q]
-                if ep != e:
-                    k.corrupt = True
+            ep, v = data[k.r][e % slots][q]
+            if ep > e:                                                   # a later epoch already sits in the slot: e is lost
+                k.corrupt = True
+                ep = e
+            if ep == e:
                 k.got[q] = v
                 k.todo.pop()
                 if not k.todo:
