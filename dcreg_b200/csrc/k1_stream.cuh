@@ -185,13 +185,17 @@ __device__ __forceinline__ bool reduce_to_fin(double mine, TailSmem& ts, double*
 #pragma unroll
         for (int w = 0; w < kWarpsPerBlock; ++w) s += ts.red[w][lane];
         partials[(size_t)block * kPk + lane] = s;
-        __threadfence();
-        __syncwarp();
-        if (lane == 0) ts.is_last = (atomicAdd(counter, 1u) == (unsigned)nblocks - 1u);
+        __syncwarp();                                             // the warp's 32 stores happen-before lane 0's release
+        if (lane == 0) {
+            // ticket with release (this block's partial row is visible before the count) and acquire (the last block
+            // sees every other block's row) semantics at GPU scope: one atomic instead of fence + atomic + fence
+            unsigned int t;
+            asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], 1;" : "=r"(t) : "l"(counter) : "memory");
+            ts.is_last = (t == (unsigned)nblocks - 1u);
+        }
     }
     __syncthreads();
     if (!ts.is_last) return false;
-    __threadfence();
     {
         constexpr int kRows = 40;                                  // rows in flight per lane and trip
         double s = 0.0;

@@ -542,8 +542,12 @@ __device__ inline void icp_step_warp_ours(const double* acc, IcpState* st, const
                                           unsigned long long* dbg = nullptr) {
     const int lane = threadIdx.x & 31;
     K2_STAMP(0);
+    // loop state (global memory): requested first, consumed only after the block inverses, which need nothing but the sums
     const int iter = st->iter;
-    dcreg_iter_log* rec = (log != nullptr && iter < log_cap) ? &log[iter] : nullptr;
+    const int warm_flag = st->warm;
+    double pre = 0.0;                                        // lanes 0..17: warm-start bases, lanes 18..29: pose
+    if (lane < 18) pre = st->V_warm[lane / 9][lane % 9];
+    else if (lane < 30) pre = lane < 27 ? st->R[lane - 18] : st->t[lane - 27];
     const int n_eff = (int)(acc[kAccNeff] + 0.5);
     const int n_pt = (int)(acc[kAccNpt] + 0.5);
     for (int e = lane; e < 36; e += 32) {
@@ -551,11 +555,24 @@ __device__ inline void icp_step_warp_ours(const double* acc, IcpState* st, const
         sm.H[e] = acc[a * 6 - (a * (a - 1)) / 2 + (b - a)];
     }
     if (lane < 6) sm.g[lane] = acc[21 + lane];
-    if (lane >= 8 && lane < 20) sm.Rt[lane - 8] = lane < 17 ? st->R[lane - 8] : st->t[lane - 17];
-    {   // warm start of the two Jacobi iterations (k2_fast.cuh); a cold start every 64 iterations bounds the drift of the
-        // accumulated rotations (5000-iteration runs, icp_iter.yaml)
-        const bool warm = st->warm != 0 && (iter & 63) != 0;
-        if (lane < 18) sm.Vw[lane / 9][lane % 9] = warm ? st->V_warm[lane / 9][lane % 9] : ((lane % 9) % 4 == 0 ? 1.0 : 0.0);
+    __syncwarp();
+    // ---- block inverses (FullPivLU semantics), lanes 0 / 1 ----
+    if (lane < 2 && n_eff >= prm.min_effective_points) {
+        double M[9];
+        const int o = lane == 0 ? 3 : 0;                     // lane 0: H_tt, lane 1: H_RR
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) M[i * 3 + j] = sm.H[(i + o) * 6 + j + o];
+        sm.ok[lane] = k2f::spd_inverse3(M, sm.inv[lane]) ? 1 : 0;   // FullPivLU::isInvertible + inverse (k2_fast.cuh)
+    }
+    // now the state: pose, warm start of the two Jacobi iterations (k2_fast.cuh; a cold start every 64 iterations bounds
+    // the drift of the accumulated rotations in 5000-iteration runs, icp_iter.yaml), log record
+    dcreg_iter_log* rec = (log != nullptr && iter < log_cap) ? &log[iter] : nullptr;
+    {
+        const bool warm = warm_flag != 0 && (iter & 63) != 0;
+        if (lane < 18) sm.Vw[lane / 9][lane % 9] = warm ? pre : ((lane % 9) % 4 == 0 ? 1.0 : 0.0);
+        else if (lane < 30) sm.Rt[lane - 18] = pre;
     }
     if (rec) {
         if (lane < 27) rec->H27[lane] = acc[lane];
@@ -578,16 +595,6 @@ __device__ inline void icp_step_warp_ours(const double* acc, IcpState* st, const
             }
         }
         return;
-    }
-    // ---- block inverses (FullPivLU semantics), lanes 0 / 1 ----
-    if (lane < 2) {
-        double M[9];
-        const int o = lane == 0 ? 3 : 0;                     // lane 0: H_tt, lane 1: H_RR
-#pragma unroll
-        for (int i = 0; i < 3; ++i)
-#pragma unroll
-            for (int j = 0; j < 3; ++j) M[i * 3 + j] = sm.H[(i + o) * 6 + j + o];
-        sm.ok[lane] = k2f::spd_inverse3(M, sm.inv[lane]) ? 1 : 0;   // FullPivLU::isInvertible + inverse (k2_fast.cuh)
     }
     __syncwarp();
     K2_STAMP(1);
