@@ -522,56 +522,74 @@ struct WarpKnnSmem {
     int opos[kSeeds], oidx[kSeeds];
 };
 
-__device__ __forceinline__ bool knn_warp_search(const Grid& g, float qx, float qy, float qz, float B, WarpKnnSmem& S,
-                                                KnnM& out, float& lb) {
-    const unsigned full = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
-    const int K = g.rings, W = 2 * K + 1, nrows = W * W;
+// One row (r of (2K+1)^2, x-fastest over (dy, dz)) of a bounded query's set-up: the point range of the row's cells that can
+// hold something within the squared bound B, and `lb`, a lower bound on the squared distance of everything it dropped
+// (3e38: dropped nothing).  A tile's searches have their rows set up by ALL its threads at once before the warps start
+// (icp_iter2_kernel): one memory round trip for the whole tile instead of one at the head of every search.
+struct RowRange { int s, e; float lb; };
+
+__device__ __forceinline__ RowRange knn_row_range(const Grid& g, float qx, float qy, float qz, float B, int r) {
+    const int K = g.rings, W = 2 * K + 1;
     const float cell = (float)(1.0 / g.inv_cell);
     const int cx = cell_coord(qx, g.inv_cell), cy = cell_coord(qy, g.inv_cell), cz = cell_coord(qz, g.inv_cell);
     const int lx = cx - g.ox, ly = cy - g.oy, lz = cz - g.oz;
     const float eps = 2e-6f * (fabsf(qx) + fabsf(qy) + fabsf(qz) + cell);
     const float fx = qx - (float)cx * cell, fy = qy - (float)cy * cell, fz = qz - (float)cz * cell;
+    RowRange out{0, 0, 3.0e38f};
+    const int rz = r / W;
+    const int dz = rz - K, dy = r - rz * W - K;
+    const int zz = lz + dz, yy = ly + dy;
+    if (zz >= 0 && zz < g.nz && yy >= 0 && yy < g.ny) {
+        const float gz = dz == 0 ? 0.0f : fmaxf((dz < 0 ? fz + (float)(-dz - 1) * cell : (cell - fz) + (float)(dz - 1) * cell) - eps, 0.0f);
+        const float gy = dy == 0 ? 0.0f : fmaxf((dy < 0 ? fy + (float)(-dy - 1) * cell : (cell - fy) + (float)(dy - 1) * cell) - eps, 0.0f);
+        const float row_lb = (gy * gy + gz * gz) * 0.99999f;
+        if (row_lb <= B) {
+            int xa = lx - K, xb = lx + K;                  // drop end cells whose box distance exceeds the bound
+#pragma unroll 1
+            for (; xa < lx; ++xa) {
+                const float gl = fmaxf(fx + (float)(lx - xa - 1) * cell - eps, 0.0f);
+                const float b = row_lb + gl * gl * 0.99999f;
+                if (b <= B) break;
+                out.lb = fminf(out.lb, b);
+            }
+#pragma unroll 1
+            for (; xb > lx; --xb) {
+                const float gr = fmaxf((cell - fx) + (float)(xb - lx - 1) * cell - eps, 0.0f);
+                const float b = row_lb + gr * gr * 0.99999f;
+                if (b <= B) break;
+                out.lb = fminf(out.lb, b);
+            }
+            xa = max(xa, 0); xb = min(xb, g.nx - 1);
+            if (xa <= xb) {
+                const int* rowp = g.cell_start + (size_t)(zz * g.ny + yy) * g.nx;
+                out.s = __ldg(rowp + xa); out.e = __ldg(rowp + xb + 1);
+            }
+        } else {
+            out.lb = row_lb;
+        }
+    }
+    return out;
+}
+
+// prof (profiling only, may be null): [0] += cycles of the row set-up, [1] += prefix + candidate scan, [2] += selection,
+// [3] += searches, [4] += candidates scanned
+__device__ __forceinline__ bool knn_warp_search(const Grid& g, float qx, float qy, float qz, float B, WarpKnnSmem& S,
+                                                KnnM& out, float& lb, long long* prof = nullptr, const RowRange* pre = nullptr) {
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    long long tc0 = 0, tc1 = 0, tc2 = 0;
+    if (prof) tc0 = clock64();
+    const int K = g.rings, W = 2 * K + 1, nrows = W * W;
     float lbl = lb;                                   // lane-local lower bound of everything this lane drops
     if (lane < kSeeds) { S.od2[lane] = B; S.opos[lane] = -1; S.oidx[lane] = 0x7fffffff; }
 #pragma unroll 1
     for (int r = lane; r < nrows; r += 32) {
-        const int rz = r / W;
-        const int dz = rz - K, dy = r - rz * W - K;
-        const int zz = lz + dz, yy = ly + dy;
-        int s = 0, e = 0;
-        if (zz >= 0 && zz < g.nz && yy >= 0 && yy < g.ny) {
-            const float gz = dz == 0 ? 0.0f : fmaxf((dz < 0 ? fz + (float)(-dz - 1) * cell : (cell - fz) + (float)(dz - 1) * cell) - eps, 0.0f);
-            const float gy = dy == 0 ? 0.0f : fmaxf((dy < 0 ? fy + (float)(-dy - 1) * cell : (cell - fy) + (float)(dy - 1) * cell) - eps, 0.0f);
-            const float row_lb = (gy * gy + gz * gz) * 0.99999f;
-            if (row_lb <= B) {
-                int xa = lx - K, xb = lx + K;                  // drop end cells whose box distance exceeds the bound
-#pragma unroll 1
-                for (; xa < lx; ++xa) {
-                    const float gl = fmaxf(fx + (float)(lx - xa - 1) * cell - eps, 0.0f);
-                    const float b = row_lb + gl * gl * 0.99999f;
-                    if (b <= B) break;
-                    lbl = fminf(lbl, b);
-                }
-#pragma unroll 1
-                for (; xb > lx; --xb) {
-                    const float gr = fmaxf((cell - fx) + (float)(xb - lx - 1) * cell - eps, 0.0f);
-                    const float b = row_lb + gr * gr * 0.99999f;
-                    if (b <= B) break;
-                    lbl = fminf(lbl, b);
-                }
-                xa = max(xa, 0); xb = min(xb, g.nx - 1);
-                if (xa <= xb) {
-                    const int* rowp = g.cell_start + (size_t)(zz * g.ny + yy) * g.nx;
-                    s = __ldg(rowp + xa); e = __ldg(rowp + xb + 1);
-                }
-            } else {
-                lbl = fminf(lbl, row_lb);
-            }
-        }
-        S.rs[r] = s; S.re[r] = e;
+        const RowRange rr = pre ? pre[r] : knn_row_range(g, qx, qy, qz, B, r);
+        lbl = fminf(lbl, rr.lb);
+        S.rs[r] = rr.s; S.re[r] = rr.e;
     }
     __syncwarp();
+    if (prof) tc1 = clock64();
     // Candidates of ALL rows as one flat list (prefix sums of the row lengths): lane l takes candidates l, l + 32, ...
     // wherever their rows are, so the point loads of different rows are independent and in flight together (walking
     // the rows one after the other costs one dependent memory round trip per row: 9 for cell = radius, up to 81).
@@ -594,8 +612,14 @@ __device__ __forceinline__ bool knn_warp_search(const Grid& g, float qx, float q
     int cnt = 0;
     bool overflow = false;
     int row = 0;                                      // row of this lane's current candidate (candidates ascend per lane)
-#pragma unroll 1
+    // cell = radius (9 rows): the prefix sums in registers, so a candidate's row is nine compares instead of a walk
+    // through shared memory with one dependent load per step
+    const bool few_rows = nrows <= 9;
+    int pr[9];
+#pragma unroll
+    for (int r = 0; r < 9; ++r) pr[r] = (few_rows && r < nrows) ? S.pref[r + 1] : 0x7fffffff;
     constexpr int kU = 4;                             // candidates per lane and trip: that many loads in flight
+#pragma unroll 1
     for (int c0 = 0; c0 < total; c0 += 32 * kU) {
         int jj[kU];
         bool in[kU];
@@ -606,13 +630,20 @@ __device__ __forceinline__ bool knn_warp_search(const Grid& g, float qx, float q
             in[u] = c < total;
             jj[u] = 0;
             if (in[u]) {
-                while (c >= S.pref[row + 1]) ++row;
+                if (few_rows) {
+                    row = 0;
+#pragma unroll
+                    for (int r = 0; r < 8; ++r) row += (c >= pr[r]) ? 1 : 0;
+                } else {
+                    while (c >= S.pref[row + 1]) ++row;
+                }
                 jj[u] = S.rs[row] + (c - S.pref[row]);
                 pp[u] = __ldg(&g.pts[jj[u]]);
             }
         }
 #pragma unroll
         for (int u = 0; u < kU; ++u) {
+            if (c0 + u * 32 >= total) break;          // (uniform) nothing left for this and the following slots
             bool hit = false;
             float d = 0.0f;
             int pi = 0;
@@ -631,23 +662,32 @@ __device__ __forceinline__ bool knn_warp_search(const Grid& g, float qx, float q
     }
     __syncwarp();
     if (overflow) return false;
+    if (prof) tc2 = clock64();
+    // Rank of every candidate inside the bound = number of candidates that precede it in (d2, index) order; ranks 0..6 are
+    // the list.  All-pairs over the (few: ~20 of ~45 scanned) hits with broadcast shared-memory reads: the iterations
+    // are independent, so unrolled they pipeline (~500 cycles).  Measured alternatives on the C2 loop (clock64 per
+    // phase, tools/timeline.py): seven warp-wide minimum extractions with REDUX 2200-2900 cycles (a serial chain of
+    // collectives), this loop not unrolled ~2000.
 #pragma unroll 1
     for (int en = lane; en < cnt; en += 32) {
         const float de = S.d2[en];
         const int ie = S.idx[en];
         int rank = 0;
-#pragma unroll 1
+#pragma unroll 4
         for (int f = 0; f < cnt; ++f) rank += knn_less(S.d2[f], S.idx[f], de, ie) ? 1 : 0;
         if (rank < kSeeds) { S.od2[rank] = de; S.opos[rank] = S.pos[en]; S.oidx[rank] = ie; }
         else lbl = fminf(lbl, de);
     }
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) lbl = fminf(lbl, __shfl_xor_sync(full, lbl, off));
+    lbl = __uint_as_float(__reduce_min_sync(full, __float_as_uint(lbl)));      // lbl >= 0: bit patterns order like the values
     __syncwarp();
 #pragma unroll
     for (int i = 0; i < kSeeds; ++i) { out.d2[i] = S.od2[i]; out.pos[i] = S.opos[i]; out.idx[i] = S.oidx[i]; }
     lb = lbl;
     __syncwarp();
+    if (prof && lane == 0) {
+        const long long tc3 = clock64();
+        prof[0] += tc1 - tc0; prof[1] += tc2 - tc1; prof[2] += tc3 - tc2; prof[3] += 1; prof[4] += total;
+    }
     return true;
 }
 

@@ -184,6 +184,7 @@ struct Iter2Smem {
     double4 plane[kBlock];
     signed char fitres[kBlock];
     int listS[kBlock], listF[kBlock];
+    corr::RowRange rowtab[kSearchListMax][9];   // cell rows of the tile's listed searches (cell = radius)
     int nS, nF;
 };
 
@@ -318,12 +319,25 @@ __global__ void __launch_bounds__(kBlock, 3) icp_iter2_kernel(const __grid_const
             const int nS = sm.nS;
             if (coherent && nS <= a.coop_max) {
                 corr::WarpKnnSmem& W = *reinterpret_cast<corr::WarpKnnSmem*>(sm.tbuf[warp]);
+                // cell = radius: the 9 cell rows of EVERY listed search are set up by all threads first (one memory round
+                // trip for the tile instead of one at the head of each of a warp's searches)
+                const bool pre_rows = g.rings == 1 && nS <= kSearchListMax;
+                if (pre_rows) {
+                    for (int e = tid; e < nS * 9; e += kBlock) {
+                        const int sidx = e / 9, r = e - sidx * 9;
+                        const float4 q = sm.q[sm.listS[sidx]];
+                        sm.rowtab[sidx][r] = corr::knn_row_range(g, q.x, q.y, q.z, q.w, r);
+                    }
+                    __syncthreads();
+                }
                 for (int w = warp; w < nS; w += kBlock / 32) {
                     const int t = sm.listS[w];
                     const float4 q = sm.q[t];
                     corr::KnnM r;
                     float lbq = a.r2_up * 0.9999f;    // nothing beyond the rings of cells is closer than the radius
-                    const bool got = corr::knn_warp_search(g, q.x, q.y, q.z, q.w, W, r, lbq);
+                    const bool got = corr::knn_warp_search(g, q.x, q.y, q.z, q.w, W, r, lbq,
+                                                           (a.stamps && warp == 0) ? reinterpret_cast<long long*>(a.stamps + (size_t)blockIdx.x * kStampSlots + 9) : nullptr,
+                                                           pre_rows ? sm.rowtab[w] : nullptr);
                     if (got) {
                         if (lane < corr::kSeeds) sm.res[t][lane] = W.opos[lane];
                         if (lane == 7) sm.res[t][7] = __float_as_int(lbq);

@@ -22,6 +22,9 @@ with Context(0) as ctx:
             print(f"   {names[k]:8s} done: min {col.min() / 1e3:6.1f}  median {np.median(col) / 1e3:6.1f}  max {col.max() / 1e3:6.1f} us after the first block start")
         d = np.diff(blocks[:, :6], axis=1)
         print("   per-phase duration, median / max over blocks (us):", "  ".join(f"{names[k + 1]} {np.median(d[:, k]) / 1e3:.1f}/{d[:, k].max() / 1e3:.1f}" for k in range(5)))
+        ws = blocks[:, 9:14].sum(axis=0).astype(float)
+        if ws[3] > 0:
+            print(f"   warp search (warp 0 of every block, {int(ws[3])} searches): set-up {ws[0] / ws[3]:.0f}  scan {ws[1] / ws[3]:.0f}  select {ws[2] / ws[3]:.0f} cycles, {ws[4] / ws[3]:.0f} candidates per search")
         lb = blocks[last]
         print(f"   last block {last}: gram done at {(lb[5] - t0) / 1e3:.1f}, reduced {(lb[6] - t0) / 1e3:.1f}, sums {(lb[7] - t0) / 1e3:.1f}, solved {(lb[8] - t0) / 1e3:.1f} us")
         print("   solve step (us): " + "  ".join(f"{n} {(solve[k + 1] - solve[k]) / 1e3:.2f}" for k, n in enumerate(["inverses", "schur+jacobi", "precond", "pcg", "update"])),
