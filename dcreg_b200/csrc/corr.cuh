@@ -816,7 +816,7 @@ __device__ __forceinline__ bool fit_plane(const Grid& g, const int (&kpos)[5], d
 // The same fit with the register-resident QR (small_la.cuh: same operations in the same order, bit-identical results).  A
 // separate function with its own register allocation: it is called from the fit work list of the loop kernel, where
 // almost nothing is live across the call (inlined into a loop body full of live state it spills; measured 3.7x slower
-// there).  Measured and rejected (round 2): the kFast variant of the QR (hardware reciprocal / rsqrt seeds instead of the
+// there).  Measured and rejected (round 2): a variant of the QR with hardware reciprocal / rsqrt seeds instead of the
 // ~30 IEEE divisions and square roots on the fit's dependent chain) makes a fit 7 -> 6 us, but on exactly rank-deficient
 // neighbourhoods (collinear lattice points) its 1-ulp differences flip the pivoted QR's rank decision, and the loop then
 // disagrees with the generic fit by one correspondence (tests/test_gpu_parity.py, lattice scene).

@@ -236,6 +236,7 @@ __global__ void __launch_bounds__(kBlock, 3) icp_iter2_kernel(const __grid_const
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const k1::Pose P = load_pose(st);
     const corr::Grid& g = A.grid;
+    const unsigned int epoch0 = peer::load_epoch(a.peer);     // (after pdl_wait: the previous launch has advanced it)
     DCREG_STAMP(0);
     // this trial's slices of the per-slot records
     int4* const rec_nn = a.nn + (size_t)trial * kNnRec * A.n;
@@ -496,7 +497,7 @@ __global__ void __launch_bounds__(kBlock, 3) icp_iter2_kernel(const __grid_const
     if (!k1s::reduce_to_fin(mine, sm.tail, A.partials + (size_t)trial * gridDim.x * k1s::kPk, A.counter + trial,
                             (int)blockIdx.x, (int)gridDim.x)) return;
     DCREG_STAMP(6);
-    peer::all_reduce32(a.peer, sm.tail.fin, sm.tail.red);
+    peer::all_reduce32(a.peer, sm.tail.fin, sm.tail.red, epoch0);
     k1s::congruence(sm.tail.fin, st->R, sm.tail.acc);
     __syncthreads();
     DCREG_STAMP(7);

@@ -267,6 +267,7 @@ __global__ void __launch_bounds__(kThreads, 2) reduce_stream_kernel(const __grid
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const PlaneT* gplane = reinterpret_cast<const PlaneT*>(a.plane);
     if (a.debug == 4) return;
+    const unsigned int epoch0 = peer::load_epoch(a.peer);
 
     double vh[21], vg[6], vr2 = 0.0, vb2 = 0.0;          // the 29 running sums of this lane's slots
 #pragma unroll
@@ -406,7 +407,7 @@ __global__ void __launch_bounds__(kThreads, 2) reduce_stream_kernel(const __grid
     if (a.peer.nranks > 1 || a.npt_override >= 0.0) {             // (uniform) host-kd-tree count, sum over ranks
         if (a.npt_override >= 0.0 && tid == 0) sm.tail.fin[kPkNpt] = a.npt_override;
         __syncthreads();
-        peer::all_reduce32(a.peer, sm.tail.fin, sm.tail.red);
+        peer::all_reduce32(a.peer, sm.tail.fin, sm.tail.red, epoch0);
     }
     congruence(sm.tail.fin, a.pose.R, a.acc);
 }

@@ -54,13 +54,19 @@ __device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long
     return v;
 }
 
+// This rank's epoch counter, to be read at KERNEL START by every thread that may end up in the last block (one L2 load,
+// long finished when the exchange needs it: not a round trip on the critical path).
+__device__ __forceinline__ unsigned int load_epoch(const View& pv) {
+    return pv.nranks > 1 ? pv.box[pv.rank]->epoch : 0u;
+}
+
 // All 256 threads of the (single) last block call this.  fin[32] (shared memory): in = this rank's packed totals,
-// out = the sum over ranks in rank order.  red: shared scratch [kMaxRanks][32].
-__device__ __forceinline__ void all_reduce32(const View& pv, double* fin, double (*red)[kVals]) {
+// out = the sum over ranks in rank order.  red: shared scratch [kMaxRanks][32].  epoch_in = load_epoch() of this launch.
+__device__ __forceinline__ void all_reduce32(const View& pv, double* fin, double (*red)[kVals], unsigned int epoch_in) {
     if (pv.nranks <= 1) return;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarps = (int)(blockDim.x >> 5);
     Mailbox* mine = pv.box[pv.rank];
-    const unsigned int e = mine->epoch + 1u;            // read by everyone before thread 0 advances it below
+    const unsigned int e = epoch_in + 1u;
     const double v = fin[lane];
     const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
     const unsigned long long tag = (unsigned long long)e << 32;

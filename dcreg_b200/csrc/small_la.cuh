@@ -8,7 +8,6 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <math.h>
-#include "k2_fast.cuh"
 
 namespace dla {
 
@@ -252,14 +251,8 @@ __host__ __device__ __noinline__ void colpiv_qr_solve(double* A, double* b, doub
 // index is a compile-time constant after unrolling: the pivot column is brought to position k with conditional
 // swaps against each later column and the rank cut `nz` becomes a predicate, so A, b and the norms stay in registers
 // instead of local memory.  Used for the 5x3 plane fit, which runs once per source slot.
-// kFast: the IEEE divisions and square roots (about 30 of them, each a ~40-instruction sequence on the dependent chain of
-// the one thread that fits a plane) are replaced by the hardware reciprocal / reciprocal-square-root seeds + Newton steps
-// (k2_fast.cuh, <= 2 ulp).  Same algorithm, same pivoting and rank decisions up to that rounding; on the host the fast
-// helpers ARE the exact operations, so tools/test_qr_reg.cu keeps checking the logic bit for bit.
-template <int M, int N, bool kFast = false>
+template <int M, int N>
 __host__ __device__ __forceinline__ void colpiv_qr_solve_reg(double (&A)[M][N], double (&b)[M], double (&x)[N]) {
-    auto q_sqrt = [](double v) { return kFast ? (v > 0.0 ? v * k2f::fast_rsqrt(v) : 0.0) : sqrt(v); };
-    auto q_div = [](double n, double d) { return kFast ? n * k2f::fast_rcp(d) : n / d; };
     const double eps = 2.220446049250313e-16;
     double normU[N], normD[N];
     int perm[N];
@@ -269,7 +262,7 @@ __host__ __device__ __forceinline__ void colpiv_qr_solve_reg(double (&A)[M][N], 
         double s = 0.0;
 #pragma unroll
         for (int i = 0; i < M; ++i) s += A[i][j] * A[i][j];
-        normU[j] = normD[j] = q_sqrt(s);
+        normU[j] = normD[j] = sqrt(s);
         perm[j] = j;
         if (normU[j] > maxn) maxn = normU[j];
     }
@@ -305,12 +298,12 @@ __host__ __device__ __forceinline__ void colpiv_qr_solve_reg(double (&A)[M][N], 
 #pragma unroll
             for (int i = k + 1; i < M; ++i) A[i][k] = 0.0;
         } else {
-            beta = q_sqrt(c0 * c0 + tail);
+            beta = sqrt(c0 * c0 + tail);
             if (c0 >= 0.0) beta = -beta;
-            const double inv = q_div(1.0, c0 - beta);
+            const double inv = 1.0 / (c0 - beta);
 #pragma unroll
             for (int i = k + 1; i < M; ++i) A[i][k] *= inv;
-            tau = q_div(beta - c0, beta);
+            tau = (beta - c0) / beta;
         }
         A[k][k] = beta;
         // apply to the remaining columns and to b
@@ -335,18 +328,18 @@ __host__ __device__ __forceinline__ void colpiv_qr_solve_reg(double (&A)[M][N], 
 #pragma unroll
         for (int j = k + 1; j < N; ++j) {
             if (normU[j] != 0.0) {
-                double t = q_div(fabs(A[k][j]), normU[j]);
+                double t = fabs(A[k][j]) / normU[j];
                 t = (1.0 + t) * (1.0 - t);
                 if (t < 0.0) t = 0.0;
-                const double r = q_div(normU[j], normD[j]);
+                const double r = normU[j] / normD[j];
                 const double t2 = t * r * r;
                 if (t2 <= downdate_thr) {
                     double s = 0.0;
 #pragma unroll
                     for (int i = k + 1; i < M; ++i) s += A[i][j] * A[i][j];
-                    normD[j] = normU[j] = q_sqrt(s);
+                    normD[j] = normU[j] = sqrt(s);
                 } else {
-                    normU[j] *= q_sqrt(t);
+                    normU[j] *= sqrt(t);
                 }
             }
         }
@@ -362,7 +355,7 @@ __host__ __device__ __forceinline__ void colpiv_qr_solve_reg(double (&A)[M][N], 
 #pragma unroll
             for (int j = i + 1; j < N; ++j)
                 if (j < nz) s -= A[i][j] * c[j];
-            c[i] = q_div(s, A[i][i]);
+            c[i] = s / A[i][i];
         }
     }
 #pragma unroll

@@ -29,4 +29,17 @@ for mode in (2, 1):
     if rank == 0:
         print(f"N={world} mode {ctx.comm_mode}: K1 over {hi - lo} slots per rank + sum over ranks: " + " ".join(f"{x:.2f}" for x in ts) + " us per launch")
     ctx.close()
+# the same shard WITHOUT any exchange (plain context): what the sum over ranks costs on top
+ctx = Context(local)
+ctx.set_target(scene, 0.05); ctx.set_source(scene[lo:hi])
+ctx.find_planes(T, 0.05, want_planes=False); ctx.freeze_planes_f32()
+ctx.time_reduce(False, T, False, 5, False)
+ts = []
+for _ in range(5):
+    dist.barrier(device_ids=[local]); torch.cuda.synchronize()
+    t = torch.tensor([ctx.time_reduce(False, T, False, 50, False)], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX); ts.append(float(t.item()) * 1e3)
+if rank == 0:
+    print(f"N={world} no exchange: K1 over {hi - lo} slots per rank alone: " + " ".join(f"{x:.2f}" for x in ts) + " us per launch")
+ctx.close()
 dist.destroy_process_group()
