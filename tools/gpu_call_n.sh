@@ -8,6 +8,7 @@ timeout 600 $TR --master-port 29711 tools/sharded_check.py > gpurun_out/sharded_
 grep -E "mode|SHARDED|Error|error" gpurun_out/sharded_$N.log | head -20
 SHARDED_CHECK_POINTS=1000000 timeout 600 $TR --master-port 29712 tools/sharded_check.py > gpurun_out/sharded_1m_$N.log 2>&1; echo "sharded_check 1M rc=$?"
 grep -E "mode|SHARDED|Error|error" gpurun_out/sharded_1m_$N.log | head -20
+timeout 600 $TR --master-port 29715 tools/sharded_reduce_time.py > gpurun_out/sharded_reduce_$N.log 2>&1; grep -E "mode|exchange" gpurun_out/sharded_reduce_$N.log
 timeout 600 $TR --master-port 29713 bench.py --gpus $N --steps 20 --warmup 3 > gpurun_out/bench_n$N.json 2> gpurun_out/bench_n$N.err; echo "bench rc=$?"
 tail -c 1500 gpurun_out/bench_n$N.err
 timeout 300 $TR --master-port 29714 bench.py --impl reference --gpus $N --steps 5 --warmup 1 > gpurun_out/ref_n$N.json 2> gpurun_out/ref_n$N.err; echo "ref rc=$?"
