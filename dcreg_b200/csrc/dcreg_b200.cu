@@ -5,11 +5,13 @@
 //   tgt grid float4[M]   target points grouped by hash-grid cell + keys/start/count tables
 //   planes64 double4[N]  (nx,ny,nz,d) per source slot, only materialised for the seams / host-plane mode
 //   planes32 float4[N]   the 32 B/slot frozen-plane layout of the K1 benchmark
-//   partials double[grid][32], acc double[32], state (pose, flags), log records
-// One ICP iteration = two kernels chained on one stream: the iteration kernel (correspondences +
-// residual + Jacobian + 27-sum reduction; the last block to finish reduces the block partials) and the
-// single-warp K2 step (analysis, solve, pose update, convergence flag), so nothing returns to the host
-// inside the loop.  Sharded over GPUs a 32-double ncclAllReduce sits between the two.
+//   per trial (dcreg_icp_run: one, dcreg_icp_run_batch: many): neighbour records / plane cache (100 B per slot),
+//   partials double[grid.x][32], acc double[32], ticket, state (pose, flags, warm-start bases), log records
+// One ICP iteration = ONE kernel (icp_iter2_kernel): correspondences + residual + Jacobian + 27-sum reduction; the block
+// that finishes a trial's reduction sums the block partials, [adds the other ranks' sums through peer-memory mailboxes,
+// peer_reduce.cuh,] and its first warp runs the K2 step (analysis, solve, pose update, convergence flag), so nothing
+// returns to the host inside the loop and the loop bodies of a run are replayed as one CUDA graph.  Baseline methods,
+// hash grids and the NCCL fallback of a sharded run keep K2 as a second kernel (k2_step_kernel).
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <math.h>
@@ -511,9 +513,10 @@ __global__ void __launch_bounds__(kBlock, 3) icp_iter2_kernel(const __grid_const
     }
 }
 
-// K2 as its own kernel (seam 3, and the sharded loop after the all-reduce).
-// K2 executes ~4 k warp instructions exactly once per launch, so it runs at instruction-fetch speed (ncu: top stall
-// no_instruction, 14 cycles per instruction).  Thanks to the programmatic dependent launch it starts while the
+// K2 as its own kernel: baseline methods (their generic single-thread step), hash-grid runs, the host-plane loop and the
+// NCCL fallback of a sharded run.  One warp per trial (blockIdx.x).
+// K2 executes a few thousand warp instructions exactly once per launch (round 1 ncu: top stall no_instruction, 14 cycles
+// per instruction).  Thanks to the programmatic dependent launch it starts while the
 // iteration kernel is still running, so it first executes the SAME code on a scratch copy of the state with the
 // previous iteration's sums (same branches, harmless stores), which pulls the instructions into the SM's caches;
 // only then does it wait for the iteration kernel and do the real step.
