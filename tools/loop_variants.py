@@ -11,7 +11,7 @@ pts = make_cylinder(100_000, seed=42)
 T0 = g2_initial_pose()
 prm = default_params(search_radius=1.0, max_iterations=50, fixed_iterations=1, kappa_target=10.0)
 with Context(0) as ctx:
-    ctx.set_target(pts, 1.0)
+    ctx.set_target(pts, float(os.environ.get("ICP_CELL", "1.0")))
     ctx.set_source(pts)
     for _ in range(3):
         res = ctx.icp_run(prm, T0, want_log=False)
