@@ -328,3 +328,49 @@ def test_host_planes_fitness_uses_the_callers_count(ctx, golden, cylinder):
         assert a.n_effective == b.n_eff and a.n_corr_pt == b.n_pt
         assert abs(a.fitness - b.fitness) < 1e-15
     assert res.logs[0].n_corr_pt == 391 and abs(res.logs[0].fitness - 0.05170590) < 1e-8   # G2, iteration 0 (shipped)
+
+
+# ------------------------------------------------------------------------------------------------
+# hash-grid fallback (bounding box too large for the dense cell table), aborting trials in a batch
+# ------------------------------------------------------------------------------------------------
+def test_hash_grid_path_matches_oracle(ctx, cylinder):
+    """Two far outliers blow the target's bounding box up to ~1e11 cells: the index falls back to the hash table, the
+    loop to the one-thread-per-slot kernel + separate solve kernel.  Same trajectory as the oracle; a batch is refused."""
+    from dcreg_b200 import default_params
+    from dcreg_b200.api import DcregError
+    from dcreg_b200.scenes import g2_initial_pose
+    tgt = np.concatenate([cylinder, np.array([[4000.0, 4500.0, 5000.0], [-4000.0, -3000.0, 2000.0]], np.float32)]).astype(np.float32)
+    T0 = g2_initial_pose()
+    prm = o.Params(kappa_target=10.0, use_weight_derivative=True)
+    conv, T_ref, logs, status = o.icp_so3(cylinder, tgt, T0, prm)
+    gp = default_params(kappa_target=10.0, use_weight_derivative=1)
+    ctx.set_target(tgt, 1.0)
+    ctx.set_source(cylinder)
+    res = ctx.icp_run(gp, T0)
+    assert res.converged == conv and res.iterations == len(logs)
+    for a, b in zip(res.logs, logs):
+        assert a.n_effective == b.n_eff and a.n_corr_pt == b.n_pt
+    assert o.se3_log_distance(T_ref, res.T) < 1e-6
+    with pytest.raises(DcregError):
+        ctx.icp_run_batch(gp, perturbations(2))
+    ctx.set_target(cylinder, 1.0)            # back to a dense grid for the tests that follow
+
+
+def test_batch_with_aborting_trials(ctx, cylinder):
+    """A trial that starts 100 m away finds no correspondences and aborts (NOT_ENOUGH_POINTS, icp_test_runner.cpp:1847)
+    without disturbing its neighbours in the batch."""
+    from dcreg_b200 import default_params
+    from dcreg_b200.api import NOT_ENOUGH_POINTS
+    gp = default_params(kappa_target=10.0, max_iterations=30)
+    Ts = perturbations(5, seed=47)
+    far = np.eye(4); far[:3, 3] = [100.0, 0.0, 50.0]
+    Ts[2] = far
+    ctx.set_target(cylinder, 1.0)
+    ctx.set_source(cylinder)
+    batch = ctx.icp_run_batch(gp, Ts, want_log=True)
+    assert batch[2].status == NOT_ENOUGH_POINTS and not batch[2].converged and batch[2].iterations == 1
+    assert np.allclose(batch[2].T, far)
+    for t in (0, 1, 3, 4):
+        single = ctx.icp_run(gp, Ts[t])
+        assert batch[t].status == single.status == 0 and batch[t].iterations == single.iterations
+        assert o.se3_log_distance(single.T, batch[t].T) < 1e-8
