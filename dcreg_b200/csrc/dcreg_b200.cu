@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(kBlock, 3) icp_iteration_kernel(const __grid_c
             corr::Knn5 nn;
             corr::knn_init(nn);
             corr::knn_search(a.grid, qx, qy, qz, nn);
-            if (nn.pos[4] >= 0 && (double)nn.d2[4] < r2max) {                // icp_test_runner.cpp:1726
+            if (nn.pos[4] >= 0 && (double)corr::knn_d2(nn, 4) < r2max) {     // icp_test_runner.cpp:1726
                 npt += 1;                                                     // :1731
                 ok = corr::fit_plane(a.grid, nn.pos, a.prm.min_normal_norm, a.prm.plane_thickness, nx, ny, nz, d);
             }
@@ -367,7 +367,7 @@ __global__ void __launch_bounds__(kBlock, 3) icp_iter2_kernel(const __grid_const
                     corr::knn_search(g, q.x, q.y, q.z, r);
 #pragma unroll
                     for (int k = 0; k < 5; ++k) sm.res[tid][k] = r.pos[k];
-                    sm.res[tid][5] = -1; sm.res[tid][6] = -1; sm.res[tid][7] = 0; sm.res[tid][8] = __float_as_int(r.d2[4]);
+                    sm.res[tid][5] = -1; sm.res[tid][6] = -1; sm.res[tid][7] = 0; sm.res[tid][8] = __float_as_int(corr::knn_d2(r, 4));
                 }
                 sm.res[tid][9] = 0;
             }
