@@ -403,21 +403,19 @@ __device__ __forceinline__ void knn_search(const Grid& g, float qx, float qy, fl
 //     (icp_iter2_kernel).
 constexpr int kSeeds = 7;
 
-struct KnnM {
-    float d2[kSeeds];
+struct KnnM {                 // as Knn5: key = (bits of the squared distance) << 32 | original index, ascending
+    unsigned long long key[kSeeds];
     int pos[kSeeds];
-    int idx[kSeeds];
 };
+__device__ __forceinline__ float knn_d2(const KnnM& k, int i) { return __uint_as_float((unsigned)(k.key[i] >> 32)); }
 
-__device__ __forceinline__ void knnm_insert(KnnM& k, float d2, int pos, int idx) {
-    k.d2[kSeeds - 1] = d2; k.pos[kSeeds - 1] = pos; k.idx[kSeeds - 1] = idx;
+__device__ __forceinline__ void knnm_insert(KnnM& k, unsigned long long key, int pos) {
+    k.key[kSeeds - 1] = key; k.pos[kSeeds - 1] = pos;
 #pragma unroll
     for (int i = kSeeds - 1; i > 0; --i) {
-        const bool sw = (k.d2[i] < k.d2[i - 1]) || (k.d2[i] == k.d2[i - 1] && k.idx[i] < k.idx[i - 1]);
-        if (sw) {
-            const float td = k.d2[i]; k.d2[i] = k.d2[i - 1]; k.d2[i - 1] = td;
+        if (k.key[i] < k.key[i - 1]) {
+            const unsigned long long tk = k.key[i]; k.key[i] = k.key[i - 1]; k.key[i - 1] = tk;
             const int tp = k.pos[i]; k.pos[i] = k.pos[i - 1]; k.pos[i - 1] = tp;
-            const int ti = k.idx[i]; k.idx[i] = k.idx[i - 1]; k.idx[i - 1] = ti;
         }
     }
 }
@@ -430,17 +428,17 @@ __device__ __forceinline__ void knn_scan_range_lb(const float4* __restrict__ pts
     for (; j + 1 < e; j += 2) {                       // two candidates per trip: both loads in flight
         const float4 p0 = __ldg(&pts[j]), p1 = __ldg(&pts[j + 1]);
         const float a0 = dist2(qx, qy, qz, p0), a1 = dist2(qx, qy, qz, p1);
-        const int i0 = __float_as_int(p0.w), i1 = __float_as_int(p1.w);
-        if (a0 < k.d2[L] || (a0 == k.d2[L] && i0 < k.idx[L])) { lb = fminf(lb, k.d2[L]); knnm_insert(k, a0, j, i0); }
+        const unsigned long long k0 = knn_key(a0, __float_as_int(p0.w)), k1 = knn_key(a1, __float_as_int(p1.w));
+        if (k0 < k.key[L]) { lb = fminf(lb, knn_d2(k, L)); knnm_insert(k, k0, j); }
         else lb = fminf(lb, a0);                      // rejected candidates and evicted entries bound the outside
-        if (a1 < k.d2[L] || (a1 == k.d2[L] && i1 < k.idx[L])) { lb = fminf(lb, k.d2[L]); knnm_insert(k, a1, j + 1, i1); }
+        if (k1 < k.key[L]) { lb = fminf(lb, knn_d2(k, L)); knnm_insert(k, k1, j + 1); }
         else lb = fminf(lb, a1);
     }
     if (j < e) {
         const float4 p0 = __ldg(&pts[j]);
         const float a0 = dist2(qx, qy, qz, p0);
-        const int i0 = __float_as_int(p0.w);
-        if (a0 < k.d2[L] || (a0 == k.d2[L] && i0 < k.idx[L])) { lb = fminf(lb, k.d2[L]); knnm_insert(k, a0, j, i0); }
+        const unsigned long long k0 = knn_key(a0, __float_as_int(p0.w));
+        if (k0 < k.key[L]) { lb = fminf(lb, knn_d2(k, L)); knnm_insert(k, k0, j); }
         else lb = fminf(lb, a0);
     }
 }
@@ -448,7 +446,7 @@ __device__ __forceinline__ void knn_scan_range_lb(const float4* __restrict__ pts
 __device__ __forceinline__ void knn_search_lb(const Grid& g, float qx, float qy, float qz, float B, KnnM& k, float& lb) {
     constexpr int L = kSeeds - 1;
 #pragma unroll
-    for (int i = 0; i < kSeeds; ++i) { k.d2[i] = B; k.pos[i] = -1; k.idx[i] = 0x7fffffff; }
+    for (int i = 0; i < kSeeds; ++i) { k.key[i] = knn_key(B, 0x7fffffff); k.pos[i] = -1; }
     const int cx = cell_coord(qx, g.inv_cell), cy = cell_coord(qy, g.inv_cell), cz = cell_coord(qz, g.inv_cell);
     const int K = g.rings;
     const float cell = (float)(1.0 / g.inv_cell);
@@ -460,7 +458,7 @@ __device__ __forceinline__ void knn_search_lb(const Grid& g, float qx, float qy,
     for (int ring = 0; ring <= K; ++ring) {
         if (ring > 1) {
             const float m = fmaxf(fminf(fminf(fy, cell - fy), fminf(fz, cell - fz)) + (float)(ring - 1) * cell - eps, 0.0f);
-            if (m * m * 0.99999f > k.d2[L]) { lb = fminf(lb, m * m * 0.99999f); break; }
+            if (m * m * 0.99999f > knn_d2(k, L)) { lb = fminf(lb, m * m * 0.99999f); break; }
         }
 #pragma unroll 1
         for (int dz = -ring; dz <= ring; ++dz) {
@@ -474,7 +472,7 @@ __device__ __forceinline__ void knn_search_lb(const Grid& g, float qx, float qy,
                 if (yy < 0 || yy >= g.ny) continue;
                 const float gy = dy == 0 ? 0.0f : fmaxf((dy < 0 ? fy + (float)(-dy - 1) * cell : (cell - fy) + (float)(dy - 1) * cell) - eps, 0.0f);
                 const float row_lb = (gy * gy + gz * gz) * 0.99999f;
-                if (row_lb > k.d2[L]) { lb = fminf(lb, row_lb); continue; }
+                if (row_lb > knn_d2(k, L)) { lb = fminf(lb, row_lb); continue; }
                 const int* rowp = g.cell_start + (size_t)(zz * g.ny + yy) * g.nx;
                 {
                     const int x0 = min(max(lx, 0), g.nx), x1 = min(max(lx + 1, 0), g.nx);
@@ -486,7 +484,7 @@ __device__ __forceinline__ void knn_search_lb(const Grid& g, float qx, float qy,
                     if (left) {
                         const float gl = fmaxf(fx + (float)(dx - 1) * cell - eps, 0.0f);
                         const float b = row_lb + gl * gl * 0.99999f;
-                        if (b <= k.d2[L]) {
+                        if (b <= knn_d2(k, L)) {
                             const int x0 = min(max(lx - dx, 0), g.nx), x1 = min(max(lx - dx + 1, 0), g.nx);
                             knn_scan_range_lb(g.pts, __ldg(rowp + x0), __ldg(rowp + x1), qx, qy, qz, k, lb);
                         } else { lb = fminf(lb, b); left = false; }
@@ -494,7 +492,7 @@ __device__ __forceinline__ void knn_search_lb(const Grid& g, float qx, float qy,
                     if (right) {
                         const float gr = fmaxf((cell - fx) + (float)(dx - 1) * cell - eps, 0.0f);
                         const float b = row_lb + gr * gr * 0.99999f;
-                        if (b <= k.d2[L]) {
+                        if (b <= knn_d2(k, L)) {
                             const int x0 = min(max(lx + dx, 0), g.nx), x1 = min(max(lx + dx + 1, 0), g.nx);
                             knn_scan_range_lb(g.pts, __ldg(rowp + x0), __ldg(rowp + x1), qx, qy, qz, k, lb);
                         } else { lb = fminf(lb, b); right = false; }
@@ -686,7 +684,7 @@ __device__ __forceinline__ bool knn_warp_search(const Grid& g, float qx, float q
     lbl = __uint_as_float(__reduce_min_sync(full, __float_as_uint(lbl)));      // lbl >= 0: bit patterns order like the values
     __syncwarp();
 #pragma unroll
-    for (int i = 0; i < kSeeds; ++i) { out.d2[i] = S.od2[i]; out.pos[i] = S.opos[i]; out.idx[i] = S.oidx[i]; }
+    for (int i = 0; i < kSeeds; ++i) { out.key[i] = knn_key(S.od2[i], S.oidx[i]); out.pos[i] = S.opos[i]; }
     lb = lbl;
     __syncwarp();
     if (prof && lane == 0) {

@@ -217,10 +217,9 @@ struct Iter2Args {
     unsigned int* stats;      // optional [2]: slots that searched, slots that refitted (profiling)
 };
 
-__device__ __forceinline__ void cswap5(float& da, int& ia, int& pa, float& db, int& ib, int& pb) {
-    if (corr::knn_less(db, ib, da, ia)) {
-        const float td = da; da = db; db = td;
-        const int ti = ia; ia = ib; ib = ti;
+__device__ __forceinline__ void cswap5(unsigned long long& ka, int& pa, unsigned long long& kb, int& pb) {
+    if (kb < ka) {                                    // one 64-bit compare = (distance, then index) order (corr::knn_key)
+        const unsigned long long tk = ka; ka = kb; kb = tk;
         const int tp = pa; pa = pb; pb = tp;
     }
 }
@@ -283,25 +282,24 @@ __global__ void __launch_bounds__(kBlock, 3) icp_iter2_kernel(const __grid_const
 #pragma unroll
                         for (int k = 0; k < corr::kSeeds; ++k) {
                             const float4 t = __ldg(&g.pts[nn.pos[k]]);
-                            nn.d2[k] = corr::dist2(qx, qy, qz, t);
-                            nn.idx[k] = __float_as_int(t.w);
+                            nn.key[k] = corr::knn_key(corr::dist2(qx, qy, qz, t), __float_as_int(t.w));
                         }
                         // 16-exchange sorting network on (d2, index)
-#define DCREG_CS(x, y) cswap5(nn.d2[x], nn.idx[x], nn.pos[x], nn.d2[y], nn.idx[y], nn.pos[y])
+#define DCREG_CS(x, y) cswap5(nn.key[x], nn.pos[x], nn.key[y], nn.pos[y])
                         DCREG_CS(0, 6); DCREG_CS(2, 3); DCREG_CS(4, 5); DCREG_CS(0, 2); DCREG_CS(1, 4); DCREG_CS(3, 6);
                         DCREG_CS(0, 1); DCREG_CS(2, 5); DCREG_CS(3, 4); DCREG_CS(1, 2); DCREG_CS(4, 6); DCREG_CS(2, 3);
                         DCREG_CS(4, 5); DCREG_CS(1, 2); DCREG_CS(3, 4); DCREG_CS(5, 6);
 #undef DCREG_CS
-                        B = fminf(B, nn.d2[6] * a.look);
+                        B = fminf(B, corr::knn_d2(nn, 6) * a.look);
                         const float ex = qx - __int_as_float(s2.x), ey = qy - __int_as_float(s2.y), ez = qz - __int_as_float(s2.z);
                         const float delta = sqrtf(ex * ex + ey * ey + ez * ez);
                         const float lb = __int_as_float(s1.w);
                         // nothing outside the seven was closer than sqrt(lb) to q_scan; it is now at least sqrt(lb) - delta away
-                        need = !((sqrtf(nn.d2[4]) + delta) * 1.00002f + 1e-7f < sqrtf(lb) * 0.99998f);
+                        need = !((sqrtf(corr::knn_d2(nn, 4)) + delta) * 1.00002f + 1e-7f < sqrtf(lb) * 0.99998f);
                         if (!need) {
 #pragma unroll
                             for (int k = 0; k < corr::kSeeds; ++k) sm.res[tid][k] = nn.pos[k];
-                            sm.res[tid][7] = s1.w; sm.res[tid][8] = __float_as_int(nn.d2[4]); sm.res[tid][9] = 1;
+                            sm.res[tid][7] = s1.w; sm.res[tid][8] = __float_as_int(corr::knn_d2(nn, 4)); sm.res[tid][9] = 1;
                         }
                     }
                 }
@@ -344,7 +342,7 @@ __global__ void __launch_bounds__(kBlock, 3) icp_iter2_kernel(const __grid_const
                     if (got) {
                         if (lane < corr::kSeeds) sm.res[t][lane] = W.opos[lane];
                         if (lane == 7) sm.res[t][7] = __float_as_int(lbq);
-                        if (lane == 8) sm.res[t][8] = __float_as_int(r.d2[4]);
+                        if (lane == 8) sm.res[t][8] = __float_as_int(corr::knn_d2(r, 4));
                         if (lane == 9) sm.res[t][9] = 0;
                     }
                     __syncwarp();
@@ -360,7 +358,7 @@ __global__ void __launch_bounds__(kBlock, 3) icp_iter2_kernel(const __grid_const
                     corr::knn_search_lb(g, q.x, q.y, q.z, q.w, r, lbq);
 #pragma unroll
                     for (int k = 0; k < corr::kSeeds; ++k) sm.res[tid][k] = r.pos[k];
-                    sm.res[tid][7] = __float_as_int(lbq); sm.res[tid][8] = __float_as_int(r.d2[4]);
+                    sm.res[tid][7] = __float_as_int(lbq); sm.res[tid][8] = __float_as_int(corr::knn_d2(r, 4));
                 } else {                              // lean: plain exact 5-NN, nothing kept for the next iteration
                     corr::Knn5 r;
                     corr::knn_init(r);
