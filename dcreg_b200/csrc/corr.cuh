@@ -504,9 +504,6 @@ __device__ __forceinline__ void knn_search_lb(const Grid& g, float qx, float qy,
     }
 }
 
-__device__ __forceinline__ bool knn_less(float d, int i, float d_ref, int i_ref) {
-    return d < d_ref || (d == d_ref && i < i_ref);
-}
 
 // ---- one query, one warp (dense grid) -----------------------------------------------------------------------------
 // Same contract as knn_search_lb, executed by all 32 lanes for ONE query: used when only a few slots of a warp need a
@@ -519,10 +516,10 @@ constexpr int kWarpKnnCap = 64;
 struct WarpKnnSmem {
     int rs[81], re[81];                              // point range per cell row (empty when pruned)
     int pref[82];                                    // exclusive prefix sums of the row lengths (+ total)
-    float d2[kWarpKnnCap];
-    int pos[kWarpKnnCap], idx[kWarpKnnCap];
-    float od2[kSeeds];
-    int opos[kSeeds], oidx[kSeeds];
+    unsigned long long key[kWarpKnnCap];             // candidates inside the bound: knn_key(d2, index), ...
+    int pos[kWarpKnnCap];                            // ... and their position
+    unsigned long long okey[kSeeds];                 // the list, ascending
+    int opos[kSeeds];
 };
 
 // One row (r of (2K+1)^2, x-fastest over (dy, dz)) of a bounded query's set-up: the point range of the row's cells that can
@@ -584,7 +581,7 @@ __device__ __forceinline__ bool knn_warp_search(const Grid& g, float qx, float q
     if (prof) tc0 = clock64();
     const int K = g.rings, W = 2 * K + 1, nrows = W * W;
     float lbl = lb;                                   // lane-local lower bound of everything this lane drops
-    if (lane < kSeeds) { S.od2[lane] = B; S.opos[lane] = -1; S.oidx[lane] = 0x7fffffff; }
+    if (lane < kSeeds) { S.okey[lane] = knn_key(B, 0x7fffffff); S.opos[lane] = -1; }
 #pragma unroll 1
     for (int r = lane; r < nrows; r += 32) {
         const RowRange rr = pre ? pre[r] : knn_row_range(g, qx, qy, qz, B, r);
@@ -658,7 +655,7 @@ __device__ __forceinline__ bool knn_warp_search(const Grid& g, float qx, float q
             }
             const unsigned bits = __ballot_sync(full, hit);
             const int slot = cnt + __popc(bits & ((1u << lane) - 1u));
-            if (hit && slot < kWarpKnnCap) { S.d2[slot] = d; S.pos[slot] = jj[u]; S.idx[slot] = pi; }
+            if (hit && slot < kWarpKnnCap) { S.key[slot] = knn_key(d, pi); S.pos[slot] = jj[u]; }
             cnt += __popc(bits);
         }
         if (cnt > kWarpKnnCap) { overflow = true; break; }
@@ -673,18 +670,17 @@ __device__ __forceinline__ bool knn_warp_search(const Grid& g, float qx, float q
     // collectives), this loop not unrolled ~2000.
 #pragma unroll 1
     for (int en = lane; en < cnt; en += 32) {
-        const float de = S.d2[en];
-        const int ie = S.idx[en];
+        const unsigned long long ke = S.key[en];
         int rank = 0;
 #pragma unroll 4
-        for (int f = 0; f < cnt; ++f) rank += knn_less(S.d2[f], S.idx[f], de, ie) ? 1 : 0;
-        if (rank < kSeeds) { S.od2[rank] = de; S.opos[rank] = S.pos[en]; S.oidx[rank] = ie; }
-        else lbl = fminf(lbl, de);
+        for (int f = 0; f < cnt; ++f) rank += (S.key[f] < ke) ? 1 : 0;
+        if (rank < kSeeds) { S.okey[rank] = ke; S.opos[rank] = S.pos[en]; }
+        else lbl = fminf(lbl, __uint_as_float((unsigned)(ke >> 32)));
     }
     lbl = __uint_as_float(__reduce_min_sync(full, __float_as_uint(lbl)));      // lbl >= 0: bit patterns order like the values
     __syncwarp();
 #pragma unroll
-    for (int i = 0; i < kSeeds; ++i) { out.key[i] = knn_key(S.od2[i], S.oidx[i]); out.pos[i] = S.opos[i]; }
+    for (int i = 0; i < kSeeds; ++i) { out.key[i] = S.okey[i]; out.pos[i] = S.opos[i]; }
     lb = lbl;
     __syncwarp();
     if (prof && lane == 0) {
