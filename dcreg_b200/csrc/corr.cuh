@@ -28,6 +28,7 @@ constexpr long long kMaxDenseCells = 1ll << 27;
 
 struct Grid {
     float4* pts;                // n target points grouped by cell
+    int* pos_of;                // [n] position in pts of the point with original index i (inverse of pts[j].w)
     int n;
     int dense;                  // 1: dense mode, 0: hash mode
     int rings;                  // ceil(search radius / cell edge): cells per direction a query must look at
@@ -193,7 +194,7 @@ __global__ void grid_scatter_kernel(const float4* __restrict__ pts, int n, const
 // sort does.  `cell_of` is indexed by the original point index (p.w): dense cell id or hash slot.
 __global__ void grid_rank_cells_kernel(const float4* __restrict__ in, int n, const int* __restrict__ cell_of,
                                        const int* __restrict__ start, const int* __restrict__ count,
-                                       float4* __restrict__ out) {
+                                       float4* __restrict__ out, int* __restrict__ pos_of) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n) return;
     const float4 p = in[j];
@@ -204,6 +205,7 @@ __global__ void grid_rank_cells_kernel(const float4* __restrict__ in, int n, con
     int rank = 0;
     for (int k = s; k < e; ++k) rank += (__float_as_int(__ldg(&in[k].w)) < me) ? 1 : 0;
     out[s + rank] = p;
+    if (pos_of) pos_of[me] = s + rank;
 }
 
 // cell of a (transformed) source point for the spatial sort of the source cloud, clamped into the target box
@@ -229,29 +231,35 @@ __global__ void source_cell_kernel(const float4* __restrict__ src, int n, Grid g
 // non-negative floats, whose bit patterns order like unsigned integers, so ONE 64-bit unsigned compare is the (distance,
 // then index) rule of the reference's tie handling - two instructions instead of four per compare in the insertion that
 // dominates the per-thread search (ncu, lean iterations: 30 % of all warp instructions on that compare).
+// The list carries no positions: a neighbour's position in g.pts is looked up from its index once, when the search is
+// over (Grid::pos_of) - one register and two moves per insertion step less.
 struct Knn5 {
     unsigned long long key[5];
-    int pos[5];     // position in g.pts
 };
 
 __device__ __forceinline__ unsigned long long knn_key(float d2, int idx) {
     return ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned long long)(unsigned)idx;
 }
 __device__ __forceinline__ float knn_d2(const Knn5& k, int i) { return __uint_as_float((unsigned)(k.key[i] >> 32)); }
+// positions of the five (-1 where the list still holds a sentinel): five independent loads, one round trip
+__device__ __forceinline__ void knn_positions(const Grid& g, const Knn5& k, int (&pos)[5]) {
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+        const int idx = (int)(unsigned)(k.key[i] & 0xffffffffull);
+        pos[i] = idx == 0x7fffffff ? -1 : __ldg(&g.pos_of[idx]);
+    }
+}
 
 __device__ __forceinline__ void knn_init(Knn5& k) {
 #pragma unroll
-    for (int i = 0; i < 5; ++i) { k.key[i] = knn_key(3.0e38f, 0x7fffffff); k.pos[i] = -1; }
+    for (int i = 0; i < 5; ++i) k.key[i] = knn_key(3.0e38f, 0x7fffffff);
 }
 
-__device__ __forceinline__ void knn_insert(Knn5& k, unsigned long long key, int pos) {
-    k.key[4] = key; k.pos[4] = pos;
+__device__ __forceinline__ void knn_insert(Knn5& k, unsigned long long key) {
+    k.key[4] = key;
 #pragma unroll
     for (int i = 4; i > 0; --i) {
-        if (k.key[i] < k.key[i - 1]) {
-            const unsigned long long tk = k.key[i]; k.key[i] = k.key[i - 1]; k.key[i - 1] = tk;
-            const int tp = k.pos[i]; k.pos[i] = k.pos[i - 1]; k.pos[i - 1] = tp;
-        }
+        if (k.key[i] < k.key[i - 1]) { const unsigned long long tk = k.key[i]; k.key[i] = k.key[i - 1]; k.key[i - 1] = tk; }
     }
 }
 
@@ -269,16 +277,16 @@ __device__ __forceinline__ void knn_scan_range(const float4* __restrict__ pts, i
         const float4 p0 = __ldg(&pts[j]), p1 = __ldg(&pts[j + 1]), p2 = __ldg(&pts[j + 2]), p3 = __ldg(&pts[j + 3]);   // thread's latency chain)
         const unsigned long long k0 = knn_key(dist2(qx, qy, qz, p0), __float_as_int(p0.w)), k1 = knn_key(dist2(qx, qy, qz, p1), __float_as_int(p1.w));
         const unsigned long long k2 = knn_key(dist2(qx, qy, qz, p2), __float_as_int(p2.w)), k3 = knn_key(dist2(qx, qy, qz, p3), __float_as_int(p3.w));
-        if (k0 < k.key[4]) knn_insert(k, k0, j);
-        if (k1 < k.key[4]) knn_insert(k, k1, j + 1);
-        if (k2 < k.key[4]) knn_insert(k, k2, j + 2);
-        if (k3 < k.key[4]) knn_insert(k, k3, j + 3);
+        if (k0 < k.key[4]) knn_insert(k, k0);
+        if (k1 < k.key[4]) knn_insert(k, k1);
+        if (k2 < k.key[4]) knn_insert(k, k2);
+        if (k3 < k.key[4]) knn_insert(k, k3);
     }
 #pragma unroll 1
     for (; j < e; ++j) {
         const float4 p0 = __ldg(&pts[j]);
         const unsigned long long k0 = knn_key(dist2(qx, qy, qz, p0), __float_as_int(p0.w));
-        if (k0 < k.key[4]) knn_insert(k, k0, j);
+        if (k0 < k.key[4]) knn_insert(k, k0);
     }
 }
 

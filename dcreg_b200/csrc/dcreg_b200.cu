@@ -132,9 +132,11 @@ __global__ void __launch_bounds__(kBlock, 3) icp_iteration_kernel(const __grid_c
             corr::Knn5 nn;
             corr::knn_init(nn);
             corr::knn_search(a.grid, qx, qy, qz, nn);
-            if (nn.pos[4] >= 0 && (double)corr::knn_d2(nn, 4) < r2max) {     // icp_test_runner.cpp:1726
+            int npos[5];
+            corr::knn_positions(a.grid, nn, npos);
+            if (npos[4] >= 0 && (double)corr::knn_d2(nn, 4) < r2max) {       // icp_test_runner.cpp:1726
                 npt += 1;                                                     // :1731
-                ok = corr::fit_plane(a.grid, nn.pos, a.prm.min_normal_norm, a.prm.plane_thickness, nx, ny, nz, d);
+                ok = corr::fit_plane(a.grid, npos, a.prm.min_normal_norm, a.prm.plane_thickness, nx, ny, nz, d);
             }
             if (a.planes_out)
                 a.planes_out[__float_as_int(p4.w)] = ok ? make_double4(nx, ny, nz, d) : make_double4(0.0, 0.0, 0.0, 0.0);
@@ -363,8 +365,10 @@ __global__ void __launch_bounds__(kBlock, 3) icp_iter2_kernel(const __grid_const
                     corr::Knn5 r;
                     corr::knn_init(r);
                     corr::knn_search(g, q.x, q.y, q.z, r);
+                    int rpos[5];
+                    corr::knn_positions(g, r, rpos);
 #pragma unroll
-                    for (int k = 0; k < 5; ++k) sm.res[tid][k] = r.pos[k];
+                    for (int k = 0; k < 5; ++k) sm.res[tid][k] = rpos[k];
                     sm.res[tid][5] = -1; sm.res[tid][6] = -1; sm.res[tid][7] = 0; sm.res[tid][8] = __float_as_int(corr::knn_d2(r, 4));
                 }
                 sm.res[tid][9] = 0;
@@ -1037,7 +1041,7 @@ int dcreg_destroy(dcreg_ctx* ctx) {
     ctx->drop_graphs();
     void* ptrs[] = {ctx->d_n_active, ctx->d_T_init, ctx->d_sort_tmp, ctx->d_src, ctx->d_stage, ctx->d_tgt, ctx->grid.keys, ctx->grid.cell_start, ctx->grid.hstart,
                     ctx->grid.hcount, ctx->d_src_sorted, ctx->d_cell_tmp, ctx->d_pt_cell, ctx->d_tile_sums,
-                    ctx->grid.pts, ctx->d_planes64, ctx->d_planes32, ctx->d_partials, ctx->d_counter, ctx->d_acc,
+                    ctx->grid.pts, ctx->grid.pos_of, ctx->d_planes64, ctx->d_planes32, ctx->d_partials, ctx->d_counter, ctx->d_acc,
                     ctx->d_state, ctx->d_log, ctx->d_small, ctx->d_analysis, ctx->d_flush, ctx->d_nn, ctx->d_plane_cache, ctx->d_fit_state, ctx->d_iter_stats, ctx->d_src_radius, ctx->d_plane_key, ctx->d_k2_scratch};
     for (void* p : ptrs)
         if (p) cudaFree(p);
@@ -1094,7 +1098,7 @@ static int device_exclusive_scan(dcreg_ctx* ctx, const int* in, long long n, int
 }
 
 static void free_grid(corr::Grid* g) {
-    void* ptrs[] = {g->keys, g->cell_start, g->hstart, g->hcount, g->pts};
+    void* ptrs[] = {g->keys, g->cell_start, g->hstart, g->hcount, g->pts, g->pos_of};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     *g = corr::Grid{};
@@ -1107,6 +1111,7 @@ static int build_grid(dcreg_ctx* ctx, const float4* d_pts, long long m, double c
     corr::Grid g{};
     g.n = (int)m; g.inv_cell = 1.0 / cell_size; g.rings = 1;
     CK(cudaMalloc(&g.pts, (size_t)m * sizeof(float4)));
+    CK(cudaMalloc(&g.pos_of, (size_t)m * sizeof(int)));
     int hb[6] = {1 << 30, 1 << 30, 1 << 30, -(1 << 30), -(1 << 30), -(1 << 30)};
     int* d_bounds = (int*)(ctx->d_small + 512);
     CK(cudaMemcpyAsync(d_bounds, hb, sizeof(hb), cudaMemcpyHostToDevice, ctx->stream));
@@ -1140,7 +1145,7 @@ static int build_grid(dcreg_ctx* ctx, const float4* d_pts, long long m, double c
         rc = device_exclusive_scan(ctx, counts, ncells + 1, g.cell_start);
         CK(cudaMalloc(&tmp_pts, (size_t)m * sizeof(float4)));
         corr::grid_scatter_kernel<<<nb, 256, 0, ctx->stream>>>(d_pts, (int)m, pt_cell, g.cell_start, fill, tmp_pts, 0);
-        corr::grid_rank_cells_kernel<<<nb, 256, 0, ctx->stream>>>(tmp_pts, (int)m, pt_cell, g.cell_start, nullptr, g.pts);
+        corr::grid_rank_cells_kernel<<<nb, 256, 0, ctx->stream>>>(tmp_pts, (int)m, pt_cell, g.cell_start, nullptr, g.pts, g.pos_of);
         ctx->launches += 3;
         e = cudaStreamSynchronize(ctx->stream);
     } else {
@@ -1159,7 +1164,7 @@ static int build_grid(dcreg_ctx* ctx, const float4* d_pts, long long m, double c
         rc = device_exclusive_scan(ctx, g.hcount, cap, g.hstart);
         CK(cudaMalloc(&tmp_pts, (size_t)m * sizeof(float4)));
         corr::grid_scatter_kernel<<<nb, 256, 0, ctx->stream>>>(d_pts, (int)m, pt_cell, g.hstart, fill, tmp_pts, 0);
-        corr::grid_rank_cells_kernel<<<nb, 256, 0, ctx->stream>>>(tmp_pts, (int)m, pt_cell, g.hstart, g.hcount, g.pts);
+        corr::grid_rank_cells_kernel<<<nb, 256, 0, ctx->stream>>>(tmp_pts, (int)m, pt_cell, g.hstart, g.hcount, g.pts, g.pos_of);
         ctx->launches += 3;
         e = cudaStreamSynchronize(ctx->stream);
     }
@@ -1280,7 +1285,7 @@ static int sort_source_by_cell(dcreg_ctx* ctx, const double T[16], const float4*
     int rc = device_exclusive_scan(ctx, counts, ncells + 1, start);
     if (rc) return rc;
     corr::grid_scatter_kernel<<<nb, 256, 0, ctx->stream>>>(ctx->d_src, (int)n, ctx->d_pt_cell, start, fill, ctx->d_sort_tmp, 0);
-    corr::grid_rank_cells_kernel<<<nb, 256, 0, ctx->stream>>>(ctx->d_sort_tmp, (int)n, ctx->d_pt_cell, start, nullptr, ctx->d_src_sorted);
+    corr::grid_rank_cells_kernel<<<nb, 256, 0, ctx->stream>>>(ctx->d_sort_tmp, (int)n, ctx->d_pt_cell, start, nullptr, ctx->d_src_sorted, nullptr);
     ctx->launches += 3;
     CK(cudaGetLastError());
     *src_out = ctx->d_src_sorted;
