@@ -14,6 +14,10 @@
 // CSV swaps its two error columns (icp_test_runner.cpp:1457-1458); unknown enum strings map to the first enumerator.
 // `Time_ms` per iteration is dcreg_iter_log::iter_time_ms, the device's own tic/toc of that iteration (the loop never
 // returns to the host between iterations).  Difference: `<method>_error.pcd` (jet-coloured visual artefact) is not written.
+//
+// Extension (not in the reference, which has no RNG - SURVEY.md §6 C5): an optional `monte_carlo:` block runs a seeded
+// perturbation study of every listed method through dcreg_icp_run_batch (all trials advance side by side on the GPU) and
+// writes monte_carlo_<method>.csv + monte_carlo_summary.txt.  Absent block = the reference's behaviour, unchanged.
 #include <algorithm>
 #include <chrono>
 #include <cmath>
@@ -24,6 +28,7 @@
 #include <iostream>
 #include <limits>
 #include <map>
+#include <random>
 #include <string>
 #include <sys/stat.h>
 #include <vector>
@@ -74,6 +79,11 @@ struct Config {                    // DCReg/include/utils.hpp:132-171
     std::map<std::string, std::pair<std::string, std::string>> test_methods;
     bool use_so3_parameterization = true;
     bool use_weight_derivative = false;     // USE_WEIGHT_DERIVATIVE (icp_test_runner.cpp:1691), optional key icp.use_weight_derivative
+    // optional block monte_carlo: (extension, BASELINE.json configs[4]): trials initial poses drawn uniformly in
+    // [-max_trans_m, max_trans_m]^3 x [-max_rot_deg, max_rot_deg]^3 (roll, pitch, yaw), std::mt19937_64(seed)
+    int mc_trials = 0;
+    unsigned long long mc_seed = 45;
+    double mc_max_trans = 1.0, mc_max_rot_deg = 3.0;
 };
 
 bool loadConfig(const std::string& filename, Config& c) {      // icp_test_runner.cpp:20-153
@@ -124,6 +134,14 @@ bool loadConfig(const std::string& filename, Config& c) {      // icp_test_runne
             }
             if (mp["tsvd"]) c.icp_params.TSVD_SINGULAR_THRESH = mp["tsvd"]["singular_threshold"].as<double>();
             if (mp["solution_remapping"]) c.icp_params.LOAM_EIGEN_THRESH = mp["solution_remapping"]["eigen_threshold"].as<double>();
+        }
+        if (y["monte_carlo"]) {
+            const auto& mc = y["monte_carlo"];
+            c.mc_trials = mc["trials"].as<int>();
+            if (mc["seed"]) c.mc_seed = (unsigned long long)mc["seed"].as<double>();
+            if (mc["max_trans_m"]) c.mc_max_trans = mc["max_trans_m"].as<double>();
+            if (mc["max_rot_deg"]) c.mc_max_rot_deg = mc["max_rot_deg"].as<double>();
+            if (c.mc_trials < 0 || c.mc_trials > 65535) throw yaml_lite::ParseError("monte_carlo.trials must be in [0, 65535]");
         }
         // icp_params.XICP_*: parsed by the reference for the (out-of-scope) XICP baseline; accepted and ignored here
         if (y["test_methods"])
@@ -236,6 +254,7 @@ public:
             std::cout << "\n=== Method: " << kv.first << " ===\nDetection: " << kv.second.first << "\nHandling: " << kv.second.second << std::endl;
             if (!runMethod(kv.first, det, hand)) { std::cerr << "Failed to run method: " << kv.first << std::endl; return false; }
         }
+        if (config_.mc_trials > 0 && !runMonteCarlo()) return false;
         finalizeStatistics();
         saveStatistics();
         saveDetailedResults();
@@ -272,14 +291,12 @@ private:
         }
     }
 
-    TestResult runSingleTest(const std::string& name, int det, int hand) {      // icp_test_runner.cpp:393-516
-        TestResult r;
-        r.method_name = name;
+    static bool isSo3Method(const std::string& name) {
         static const char* so3_names[] = {"Ours", "NONE", "ME-SR", "FCN-SR", "ME-TSVD", "ME-TReg"};
-        if (std::find_if(std::begin(so3_names), std::end(so3_names), [&](const char* s) { return name == s; }) == std::end(so3_names)) {
-            std::cout << "Can not recognize the method!!!!! pls check your yaml!!!" << std::endl;
-            return r;
-        }
+        return std::find_if(std::begin(so3_names), std::end(so3_names), [&](const char* s) { return name == s; }) != std::end(so3_names);
+    }
+
+    dcreg_icp_params engineParams(int det, int hand) const {
         dcreg_icp_params p;
         dcreg_default_params(&p);
         p.search_radius = config_.search_radius; p.max_iterations = config_.max_iterations;
@@ -288,6 +305,74 @@ private:
         p.cond_thresh = config_.icp_params.DEGENERACY_THRES_COND; p.eig_thresh = config_.icp_params.DEGENERACY_THRES_EIG;
         p.kappa_target = config_.icp_params.KAPPA_TARGET; p.pcg_tol = config_.icp_params.PCG_TOLERANCE;
         p.pcg_max_iter = config_.icp_params.PCG_MAX_ITER; p.std_reg_gamma = config_.icp_params.STD_REG_GAMMA;
+        return p;
+    }
+
+    // The perturbation study (extension, see the file header): one dcreg_icp_run_batch call per method.
+    bool runMonteCarlo() {
+        const int n = config_.mc_trials;
+        std::mt19937_64 gen(config_.mc_seed);
+        auto uni = [&](double a) { return ((double)(gen() >> 11) * (1.0 / 9007199254740992.0) * 2.0 - 1.0) * a; };   // [-a, a)
+        std::vector<Pose6D> init((size_t)n);
+        std::vector<double> T0((size_t)n * 16), T1((size_t)n * 16);
+        for (int i = 0; i < n; ++i) {
+            Pose6D& q = init[i];
+            q.x = uni(config_.mc_max_trans); q.y = uni(config_.mc_max_trans); q.z = uni(config_.mc_max_trans);
+            q.roll = deg2rad(uni(config_.mc_max_rot_deg)); q.pitch = deg2rad(uni(config_.mc_max_rot_deg)); q.yaw = deg2rad(uni(config_.mc_max_rot_deg));
+            const Mat4 T = pose6d_to_matrix(q);
+            std::memcpy(&T0[(size_t)i * 16], T.m, sizeof(T.m));
+        }
+        std::ofstream summary(config_.output_folder + "monte_carlo_summary.txt");
+        summary << "Perturbation Monte-Carlo: " << n << " trials, seed " << config_.mc_seed << ", |t| <= " << config_.mc_max_trans
+                << " m per axis, |rpy| <= " << config_.mc_max_rot_deg << " deg per axis\n\n";
+        summary << std::setw(15) << "Method" << std::setw(12) << "Converged%" << std::setw(12) << "Failed" << std::setw(14) << "MeanTrans(m)"
+                << std::setw(14) << "MedTrans(m)" << std::setw(14) << "MeanRot(deg)" << std::setw(14) << "MedRot(deg)" << std::setw(12) << "Avg_Iters"
+                << std::setw(12) << "Time(ms)" << std::setw(12) << "Trials/s\n";
+        for (const auto& kv : config_.test_methods) {
+            if (!isSo3Method(kv.first)) continue;
+            const dcreg_icp_params p = engineParams(detection_from_string(kv.second.first), handling_from_string(kv.second.second));
+            std::vector<int> iters((size_t)n), conv((size_t)n), status((size_t)n);
+            const auto t0 = std::chrono::high_resolution_clock::now();
+            if (!check(dcreg_icp_run_batch(ctx_, &p, n, T0.data(), T1.data(), iters.data(), conv.data(), status.data(), nullptr, 0), "icp_run_batch")) return false;
+            const double ms = std::chrono::duration<double, std::milli>(std::chrono::high_resolution_clock::now() - t0).count();
+            std::ofstream f(config_.output_folder + "monte_carlo_" + kv.first + ".csv");
+            f << "Trial,Init_x,Init_y,Init_z,Init_roll_deg,Init_pitch_deg,Init_yaw_deg,Converged,Iterations,Status,Trans_Error_m,Rot_Error_deg";
+            for (int k = 0; k < 12; ++k) f << ",T" << k / 4 << k % 4;
+            f << "\n" << std::setprecision(17);
+            std::vector<double> te, re;
+            long long it_sum = 0; int n_conv = 0, n_fail = 0;
+            for (int i = 0; i < n; ++i) {
+                Mat4 Tf; std::memcpy(Tf.m, &T1[(size_t)i * 16], sizeof(Tf.m));
+                const PoseError e = calculatePoseError(config_.gt_matrix, Tf);
+                f << i << ',' << init[i].x << ',' << init[i].y << ',' << init[i].z << ',' << rad2deg(init[i].roll) << ',' << rad2deg(init[i].pitch) << ','
+                  << rad2deg(init[i].yaw) << ',' << conv[i] << ',' << iters[i] << ',' << status[i] << ',' << e.translation_error << ',' << e.rotation_error;
+                for (int k = 0; k < 12; ++k) f << ',' << Tf.m[k];
+                f << "\n";
+                if (status[i] != DCREG_OK) { ++n_fail; continue; }
+                te.push_back(e.translation_error); re.push_back(e.rotation_error);
+                it_sum += iters[i]; n_conv += conv[i] != 0;
+            }
+            auto mean = [](const std::vector<double>& v) { double s = 0; for (double x : v) s += x; return v.empty() ? 0.0 : s / (double)v.size(); };
+            auto median = [](std::vector<double> v) { if (v.empty()) return 0.0; std::sort(v.begin(), v.end()); return v[v.size() / 2]; };
+            const double ok = (double)std::max<size_t>(1, te.size());
+            summary << std::setw(15) << kv.first << std::fixed << std::setw(12) << std::setprecision(1) << 100.0 * n_conv / (double)n << std::setw(12) << n_fail
+                    << std::setw(14) << std::setprecision(6) << mean(te) << std::setw(14) << median(te) << std::setw(14) << mean(re) << std::setw(14) << median(re)
+                    << std::setw(12) << std::setprecision(1) << (double)it_sum / ok << std::setw(12) << std::setprecision(2) << ms
+                    << std::setw(12) << std::setprecision(0) << 1000.0 * n / ms << "\n";
+            std::cout << "Monte-Carlo " << kv.first << ": " << n << " trials in " << ms << " ms, " << n_conv << " converged, " << n_fail << " aborted" << std::endl;
+        }
+        std::cout << "Monte-Carlo results saved to " << config_.output_folder << "monte_carlo_summary.txt" << std::endl;
+        return true;
+    }
+
+    TestResult runSingleTest(const std::string& name, int det, int hand) {      // icp_test_runner.cpp:393-516
+        TestResult r;
+        r.method_name = name;
+        if (!isSo3Method(name)) {
+            std::cout << "Can not recognize the method!!!!! pls check your yaml!!!" << std::endl;
+            return r;
+        }
+        dcreg_icp_params p = engineParams(det, hand);
         std::vector<dcreg_iter_log> log((size_t)std::max(1, config_.max_iterations));
         int n_iter = 0, converged = 0;
         const auto t0 = std::chrono::high_resolution_clock::now();
@@ -672,7 +757,8 @@ int dumpConfig(const std::string& config_file) {
               << "\nDEGENERACY_THRES_COND=" << c.icp_params.DEGENERACY_THRES_COND << "\nDEGENERACY_THRES_EIG=" << c.icp_params.DEGENERACY_THRES_EIG
               << "\nSTD_REG_GAMMA=" << c.icp_params.STD_REG_GAMMA << "\nKAPPA_TARGET=" << c.icp_params.KAPPA_TARGET << "\nPCG_TOLERANCE="
               << c.icp_params.PCG_TOLERANCE << "\nPCG_MAX_ITER=" << c.icp_params.PCG_MAX_ITER << "\nTSVD_SINGULAR_THRESH="
-              << c.icp_params.TSVD_SINGULAR_THRESH << "\nLOAM_EIGEN_THRESH=" << c.icp_params.LOAM_EIGEN_THRESH << "\n";
+              << c.icp_params.TSVD_SINGULAR_THRESH << "\nLOAM_EIGEN_THRESH=" << c.icp_params.LOAM_EIGEN_THRESH << "\nmc_trials=" << c.mc_trials
+              << "\nmc_seed=" << c.mc_seed << "\nmc_max_trans=" << c.mc_max_trans << "\nmc_max_rot_deg=" << c.mc_max_rot_deg << "\n";
     std::cout << "initial_matrix=";
     for (int i = 0; i < 16; ++i) std::cout << c.initial_matrix.m[i] << (i < 15 ? "," : "\n");
     std::cout << "gt_matrix=";

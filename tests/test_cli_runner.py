@@ -33,7 +33,7 @@ def runner():
     return b.build_runner()
 
 
-def write_config(path, out_dir, setup, methods, extra_methods=""):
+def write_config(path, out_dir, setup, methods, extra_methods="", extra=""):
     x, y, z = setup["init_xyz"]
     r, p, w = setup["init_rpy_deg"]
     lines = "\n".join(f'  "{m}": [ "{METHODS[m][0]}", "{METHODS[m][1]}" ]' for m in methods)
@@ -107,6 +107,7 @@ test_methods:
 #  "None": [ "NONE_DETE", "NONE_HAND" ]
 {lines}
 {extra_methods}
+{extra}
 """)
 
 
@@ -140,6 +141,21 @@ def test_yaml_config_parses_like_the_reference(runner, golden, tmp_path):
     assert [m[0] for m in methods] == ["FCN-SR", "ME-SR", "Ours", "XICP"]
     assert methods[0][3:] == ["4", "4"] and methods[1][3:] == ["2", "4"] and methods[2][3:] == ["1", "3"]
     assert methods[3][3:] == ["0", "0"]
+
+
+def test_yaml_monte_carlo_block(runner, golden, tmp_path):
+    """The optional perturbation-study block (an extension; absent = off, like the reference)."""
+    cfg = tmp_path / "icp.yaml"
+    write_config(cfg, tmp_path / "out", golden["G2"]["setup"], ["Ours"])
+    kv, _ = dump(runner, str(cfg))
+    assert kv["mc_trials"] == "0" and kv["mc_seed"] == "45"
+    write_config(cfg, tmp_path / "out", golden["G2"]["setup"], ["Ours"],
+                 extra="monte_carlo:\n  trials: 64\n  seed: 7\n  max_trans_m: 0.5\n  max_rot_deg: 2.0\n")
+    kv, _ = dump(runner, str(cfg))
+    assert kv["mc_trials"] == "64" and kv["mc_seed"] == "7" and float(kv["mc_max_trans"]) == 0.5 and float(kv["mc_max_rot_deg"]) == 2.0
+    write_config(cfg, tmp_path / "out", golden["G2"]["setup"], ["Ours"], extra="monte_carlo:\n  trials: 70000\n")
+    res = subprocess.run([runner, "--dump-config", str(cfg)], capture_output=True, text=True)
+    assert res.returncode != 0 and "monte_carlo.trials" in res.stderr
 
 
 def test_yaml_missing_required_key_fails(runner, tmp_path):
@@ -254,3 +270,44 @@ def test_runner_reproduces_shipped_iteration_csv(runner, golden, tmp_path, setup
     Tf = np.array(g["iterations"][first][-1]["T"]).reshape(4, 4)
     src = o.read_pcd_xyz(os.path.join(GOLD, "cylinder_7562.pcd")).astype(np.float64)
     assert np.abs(aligned - (src @ Tf[:3, :3].T + Tf[:3, 3])).max() < 1e-4
+
+
+@pytest.mark.gpu
+def test_runner_monte_carlo_matches_the_batched_api(runner, golden, tmp_path):
+    """monte_carlo: block of the CLI = dcreg_icp_run_batch on the poses it drew (written to the CSV) - same poses through
+    the Python binding must give the same iterations / flags and poses to 1e-8 (trial 0 sorts the source, see the header),
+    and a handful of trials are checked against the oracle loop."""
+    from dcreg_b200 import api, default_params
+    g = golden["G2"]
+    cfg = tmp_path / "icp.yaml"
+    out_dir = tmp_path / "out"
+    write_config(cfg, out_dir, g["setup"], ["Ours", "ME-TSVD"],
+                 extra="monte_carlo:\n  trials: 48\n  seed: 11\n  max_trans_m: 0.6\n  max_rot_deg: 2.0\n")
+    res = subprocess.run([runner, str(cfg)], capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    summary = (out_dir / "monte_carlo_summary.txt").read_text()
+    assert "48 trials, seed 11" in summary and "Ours" in summary and "ME-TSVD" in summary
+    pts = o.read_pcd_xyz(os.path.join(GOLD, "cylinder_7562.pcd"))
+    d = math.pi / 180
+    with api.Context() as ctx:
+        ctx.set_source(pts)
+        ctx.set_target(pts, g["setup"]["search_radius"])
+        for m in ("Ours", "ME-TSVD"):
+            rows = read_csv(out_dir / f"monte_carlo_{m}.csv")
+            assert len(rows) == 48 and [int(r["Trial"]) for r in rows] == list(range(48))
+            init = np.array([o.pose6d_to_matrix(float(r["Init_x"]), float(r["Init_y"]), float(r["Init_z"]), float(r["Init_roll_deg"]) * d,
+                                                float(r["Init_pitch_deg"]) * d, float(r["Init_yaw_deg"]) * d) for r in rows])
+            assert np.abs(init[:, :3, 3]).max() <= 0.6 and np.abs(init[:, :3, 3]).max() > 0.3     # the draws fill the box
+            s = g["setup"]
+            p = default_params(search_radius=s["search_radius"], max_iterations=s["max_iterations"], detection=METHODS[m][0],
+                               handling=METHODS[m][1], use_weight_derivative=int(s["use_weight_derivative"]),
+                               conv_thresh_rot=s["conv_rot"], conv_thresh_trans=s["conv_trans"], cond_thresh=s["cond_thresh"],
+                               eig_thresh=s["eig_thresh"], kappa_target=s["kappa_target"], std_reg_gamma=s["std_reg_gamma"])
+            res = ctx.icp_run_batch(p, init)
+            for i, r in enumerate(rows):
+                Tc = np.array([float(r[f"T{k // 4}{k % 4}"]) for k in range(12)]).reshape(3, 4)
+                assert int(r["Iterations"]) == res[i].iterations and int(r["Converged"]) == int(res[i].converged), (m, i)
+                assert int(r["Status"]) == res[i].status, (m, i)
+                assert np.abs(Tc - res[i].T[:3]).max() < 1e-8, (m, i)
+                te = float(np.linalg.norm(Tc[:, 3]))
+                assert abs(float(r["Trans_Error_m"]) - te) < 1e-9                              # gt = identity in this config
