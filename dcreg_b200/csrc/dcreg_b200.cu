@@ -217,6 +217,7 @@ struct Iter2Args {
     float r2_up;              // search radius^2 rounded up to float
     float look;               // squared-distance look-ahead beyond the seed bound (kNnLook)
     unsigned int* stats;      // optional [2]: slots that searched, slots that refitted (profiling)
+    int tile;                 // source slots per block and pass (<= kBlock; plan_iteration: chosen so the blocks fill whole SM rounds)
 };
 
 __device__ __forceinline__ void cswap5(unsigned long long& ka, int& pa, unsigned long long& kb, int& pb) {
@@ -258,9 +259,9 @@ __global__ void __launch_bounds__(kBlock, 3) icp_iter2_kernel(const __grid_const
     {
         // ---- 256-slot tiles with per-tile work lists, so that searches and fits run densely packed.  Lean mode (the
         // pose still moves a lot) uses the same phases: every slot searches (plain 5-NN), every accepted slot fits.
-        for (long long base = (long long)blockIdx.x * kBlock; base < A.n; base += (long long)gridDim.x * kBlock) {
+        for (long long base = (long long)blockIdx.x * a.tile; base < A.n; base += (long long)gridDim.x * a.tile) {
             const long long i = base + tid;
-            const bool valid = i < A.n;
+            const bool valid = tid < a.tile && i < A.n;
             if (tid == 0) { sm.nS = 0; sm.nF = 0; }
             __syncthreads();
             // -- 1. query, previous seven, certificate
@@ -1346,10 +1347,24 @@ static int plan_iteration(dcreg_ctx* ctx, const dcreg_icp_params* prm, const flo
             ctx->nn_valid = false;
         }
         // blocks per trial: one 256-slot tile per block while the whole launch fits the resident slots (3 per SM)
+        // A small cloud would leave most SMs idle (7 562 points = 30 tiles of 256): every phase of the kernel is a latency
+        // chain per tile, so a single trial is cut into >= 2 tiles per SM instead (32-slot granularity; the block keeps
+        // its 8 warps, which share the tile's searches and fits).  Measured (tools/tile_sweep.py): 47.3 -> 36.1 us per
+        // iteration on the shipped cloud; no effect once there is a tile per SM (C2: 54.7 us at 256, 232 and 226).
         long long gx = (slots + kBlock - 1) / kBlock;
-        if (trials == 1) { const long long cap = (long long)ctx->sm_count * 3; if (gx > cap) gx = cap; }
-        else if (gx > 64) gx = 64;
+        int tile = kBlock;
+        if (trials == 1) {
+            const long long cap = (long long)ctx->sm_count * 3;
+            if (gx > cap) gx = cap;
+            else {
+                if (gx < ctx->sm_count) tile = (int)std::max<long long>(32, (slots / (2LL * ctx->sm_count) + 31) / 32 * 32);
+                if (const char* e = getenv("DCREG_TILE")) tile = atoi(e);            // measurement switch
+                if (tile < 32 || tile > kBlock || (slots + tile - 1) / tile > cap) tile = kBlock;
+                gx = (slots + tile - 1) / tile;
+            }
+        } else if (gx > 64) gx = 64;
         L.grid_x = (int)gx;
+        L.b.tile = tile;
         int rc = ensure_partials(ctx, L.grid_x * trials);
         if (rc) return rc;
         a.partials = ctx->d_partials;

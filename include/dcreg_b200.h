@@ -215,7 +215,8 @@ int dcreg_icp_fetch(dcreg_ctx* ctx, double T_out[16], int* n_iterations, int* co
  * n_trials ints (status[t] = what dcreg_icp_run would have returned for trial t; any may be NULL except T_init, T_out);
  * log: n_trials x log_cap records (trial-major) or NULL.  Every trial runs the kernels a dcreg_icp_run from the same
  * T_init runs: counts, masks and iteration counts are identical, poses equal up to the order of the FP64 sums (the
- * source is sorted by target cell once, under trial 0's pose; trial 0 is bit-identical to its single run).  Not
+ * source is sorted by target cell once, under trial 0's pose, and a single run of a small cloud uses smaller tiles;
+ * 1e-8 on the poses in the tests; a batch itself is reproducible bit for bit).  Not
  * available on a sharded context: trials are independent, distribute them over ranks instead.  Needs the dense grid. */
 int dcreg_icp_run_batch(dcreg_ctx* ctx, const dcreg_icp_params* params, int n_trials, const double* T_init,
                         double* T_out, int* n_iterations, int* converged, int* status, dcreg_iter_log* log,

