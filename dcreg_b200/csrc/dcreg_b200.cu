@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(kBlock, 3) icp_iteration_kernel(const __grid_c
 //      the 8th candidate is far), or the search radius on the first iteration.
 //   4. neighbour record to HBM (next iteration's seeds); plane fit to the first five, reused while the ordered
 //      list of five stays the same (same five rows in the same order give the same QR bit for bit); residual /
-//      weight / Jacobian row; DMMA Gram accumulation.  Searches and fits of a 256-slot tile go through work lists.
+//      weight / Jacobian row; DMMA Gram accumulation.  Searches and fits of a tile (<= 256 slots, Iter2Args::tile) go through work lists.
 // Tail: packed per-block partial, atomic ticket, last block reduces (k1s::finish_packed).
 // Record per slot (3 int4): {pos0..pos3}, {pos4..pos6, bits(lb8)}, {bits(q_scan.xyz), flags};
 // pos = position in the grid's point array (ascending (d2, index) at the time of writing), -1 = none.
@@ -175,13 +175,13 @@ constexpr double kCoherentStep = 0.05;        // records are used once no source
 constexpr int kStampSlots = 16;                // per-block phase time stamps of the loop kernel (profiling only)
 #define DCREG_STAMP(k) do { if (a.stamps && tid == 0) a.stamps[(size_t)blockIdx.x * kStampSlots + (k)] = k2::globaltimer_ns(); } while (0)
 
-constexpr int kSearchListMax = 96;            // more searching slots than this in a 256-slot tile: every thread searches for itself
+constexpr int kSearchListMax = 96;            // more searching slots than this in a tile: every thread searches for itself
 
 struct Iter2Smem {
     double tbuf[kBlock / 32][8 * k1::kTRow];    // per-warp DMMA transpose buffers (also: corr::WarpKnnSmem, the warp's Gram,
                                                 // and - in the last block, after the reduction - k2::WarpSmem)
     k1s::TailSmem tail;
-    // coherent mode, per 256-slot tile
+    // coherent mode, per tile (<= kBlock slots)
     float4 q[kBlock];                           // query (x, y, z), w = search bound B
     int res[kBlock][10];                        // pos0..pos6, bits(lb), bits(d2 of the 5th), 1 = no search / 0 = searched / 2 = search pending
     int key[kBlock][5];                         // the five positions in distance order (slots that need a fit)
@@ -257,7 +257,7 @@ __global__ void __launch_bounds__(kBlock, 3) icp_iter2_kernel(const __grid_const
     unsigned n_search = 0, n_fit = 0;
     const double r2max = A.prm.search_radius * A.prm.search_radius;
     {
-        // ---- 256-slot tiles with per-tile work lists, so that searches and fits run densely packed.  Lean mode (the
+        // ---- tiles of a.tile (<= 256) slots with per-tile work lists, so that searches and fits run densely packed.  Lean mode (the
         // pose still moves a lot) uses the same phases: every slot searches (plain 5-NN), every accepted slot fits.
         for (long long base = (long long)blockIdx.x * a.tile; base < A.n; base += (long long)gridDim.x * a.tile) {
             const long long i = base + tid;
@@ -1346,7 +1346,7 @@ static int plan_iteration(dcreg_ctx* ctx, const dcreg_icp_params* prm, const flo
             ctx->nn_cap = slots; ctx->nn_trials = trials;
             ctx->nn_valid = false;
         }
-        // blocks per trial: one 256-slot tile per block while the whole launch fits the resident slots (3 per SM)
+        // blocks per trial: one tile per block while the whole launch fits the resident slots (3 per SM)
         // A small cloud would leave most SMs idle (7 562 points = 30 tiles of 256): every phase of the kernel is a latency
         // chain per tile, so a single trial is cut into >= 2 tiles per SM instead (32-slot granularity; the block keeps
         // its 8 warps, which share the tile's searches and fits).  Measured (tools/tile_sweep.py): 47.3 -> 36.1 us per
