@@ -28,6 +28,7 @@
 #include "k1_reduce.cuh"
 #include "k1_stream.cuh"
 #include "k2_solve.cuh"
+#include "loop_plan.hpp"
 #include "peer_reduce.cuh"
 
 using k2::IcpState;
@@ -1346,25 +1347,11 @@ static int plan_iteration(dcreg_ctx* ctx, const dcreg_icp_params* prm, const flo
             ctx->nn_cap = slots; ctx->nn_trials = trials;
             ctx->nn_valid = false;
         }
-        // blocks per trial: one tile per block while the whole launch fits the resident slots (3 per SM)
-        // A small cloud would leave most SMs idle (7 562 points = 30 tiles of 256): every phase of the kernel is a latency
-        // chain per tile, so a single trial is cut into >= 2 tiles per SM instead (32-slot granularity; the block keeps
-        // its 8 warps, which share the tile's searches and fits).  Measured (tools/tile_sweep.py): 47.3 -> 36.1 us per
-        // iteration on the shipped cloud; no effect once there is a tile per SM (C2: 54.7 us at 256, 232 and 226).
-        long long gx = (slots + kBlock - 1) / kBlock;
-        int tile = kBlock;
-        if (trials == 1) {
-            const long long cap = (long long)ctx->sm_count * 3;
-            if (gx > cap) gx = cap;
-            else {
-                if (gx < ctx->sm_count) tile = (int)std::max<long long>(32, (slots / (2LL * ctx->sm_count) + 31) / 32 * 32);
-                if (const char* e = getenv("DCREG_TILE")) tile = atoi(e);            // measurement switch
-                if (tile < 32 || tile > kBlock || (slots + tile - 1) / tile > cap) tile = kBlock;
-                gx = (slots + tile - 1) / tile;
-            }
-        } else if (gx > 64) gx = 64;
-        L.grid_x = (int)gx;
-        L.b.tile = tile;
+        // blocks per trial and slots per block: loop_plan.hpp
+        const char* tile_env = trials == 1 ? getenv("DCREG_TILE") : nullptr;            // measurement switch
+        const loop_plan::Tiles tp = loop_plan::plan_tiles(slots, trials, ctx->sm_count, kBlock, tile_env ? atoi(tile_env) : 0);
+        L.grid_x = (int)tp.grid_x;
+        L.b.tile = tp.tile;
         int rc = ensure_partials(ctx, L.grid_x * trials);
         if (rc) return rc;
         a.partials = ctx->d_partials;

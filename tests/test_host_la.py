@@ -34,3 +34,17 @@ def test_fast_solve_step_pieces_on_the_host(tmp_path):
     res = subprocess.run([str(exe)], capture_output=True, text=True)
     assert res.returncode == 0, res.stdout + res.stderr
     assert "K2_FAST_OK" in res.stdout
+
+
+def test_loop_tile_plan(tmp_path):
+    """loop_plan.hpp (how a run's source slots are cut into blocks of the iteration kernel) as plain host C++: coverage,
+    tile bounds, resident-block cap, the small-cloud rule and the values used for the shipped cloud / C2 / C4 / C5."""
+    gxx = shutil.which("g++")
+    if not gxx:
+        pytest.skip("g++ not available")
+    exe = tmp_path / "test_loop_plan"
+    subprocess.run([gxx, "-O2", "-std=c++17", "-o", str(exe), os.path.join(ROOT, "tools", "test_loop_plan.cpp")], check=True,
+                   capture_output=True, text=True)
+    res = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert "LOOP_PLAN_OK" in res.stdout
